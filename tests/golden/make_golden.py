@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REFERENCE in the build container.
+
+    python tests/golden/make_golden.py
+
+The reference holds no golden vectors for this path, so its own
+outputs on seeded inputs are the pin.  Inputs are stored next to outputs so the files
+are self-contained; library versions are stored in ``versions``.  Nothing here runs on
+the GPU box.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import refshim  # noqa: E402
+
+
+def versions() -> str:
+    import cv2, scipy, sklearn
+    return json.dumps({"numpy": np.__version__, "cv2": cv2.__version__, "scipy": scipy.__version__,
+                       "torch": torch.__version__, "sklearn": sklearn.__version__})
+
+
+def weather_cases():
+    pre = refshim.preprocessing()
+    out = {"versions": versions()}
+    shapes = {"s": (40, 56), "m": (96, 160)}
+    for tag, (h, w) in shapes.items():
+        np.random.seed(7)
+        image = np.random.randint(0, 255, (h, w, 3), dtype=np.uint8)
+        out[f"{tag}_image"] = image
+        for kind in ("fog", "rain", "snow", "night"):
+            for seed, intensity in ((42, None), (43, 0.5), (44, 0.9)):
+                t = pre.WeatherDegradationTransforms(seed=seed)
+                res = t.apply_weather_effect(image.copy(), kind, intensity)
+                out[f"{tag}_{kind}_seed{seed}"] = res
+        t = pre.WeatherDegradationTransforms(seed=11)
+        out[f"{tag}_depth_seed11"] = t._generate_synthetic_depth(h, w)
+    # many short streaks hugging the borders (thick-line clipping)
+    np.random.seed(3)
+    image = np.random.randint(0, 255, (24, 32, 3), dtype=np.uint8)
+    out["b_image"] = image
+    for seed in (1, 2, 3):
+        t = pre.WeatherDegradationTransforms(seed=seed)
+        out[f"b_rain_seed{seed}"] = t.apply_weather_effect(image.copy(), "rain", 0.8)
+        t = pre.WeatherDegradationTransforms(seed=seed)
+        out[f"b_snow_seed{seed}"] = t.apply_weather_effect(image.copy(), "snow", 0.7)
+    np.savez_compressed(os.path.join(HERE, "weather.npz"), **out)
+
+
+def metric_cases():
+    met = refshim.metrics()
+    out = {"versions": versions()}
+    torch.manual_seed(42)
+    # the reference's own (unused) conftest fixture shape: tests/conftest.py:192-209
+    cases = {
+        "c5": (2, 5, 64, 128, torch.int64, 0.0),
+        "c19_i64_ign": (1, 19, 48, 64, torch.int64, 0.02),
+        "c19_u8": (2, 19, 32, 48, torch.uint8, 0.0),
+    }
+    for tag, (b, c, h, w, ldt, ign) in cases.items():
+        la = torch.randn(b, c, h, w)
+        lb = torch.randn(b, c, h, w) * 1.5 + 0.3 * la
+        tgt = torch.randint(0, c, (b, h, w)).to(ldt)
+        if ign > 0:
+            tgt[torch.rand(b, h, w) < ign] = 255
+        out[f"{tag}_la"] = la.numpy()
+        out[f"{tag}_lb"] = lb.numpy()
+        out[f"{tag}_target"] = tgt.numpy()
+        iou_m = met.IoUMetrics(c)
+        r = iou_m.compute_iou(la, tgt)
+        out[f"{tag}_mean_iou"] = np.float64(r["mean_iou"])
+        out[f"{tag}_per_class_iou"] = r["per_class_iou"]
+        out[f"{tag}_valid_classes"] = r["valid_classes"]
+        out[f"{tag}_pixel_accuracy"] = np.float64(iou_m.compute_pixel_accuracy(la, tgt))
+        cal = met.ConfidenceCalibration()
+        d = cal.compute_ece(la, tgt, return_details=True)
+        out[f"{tag}_ece"] = np.float64(d["ece"])
+        out[f"{tag}_ece_scalar"] = np.float64(cal.compute_ece(la, tgt))
+        for key in ("accuracy", "confidence", "proportion", "error", "bin_lower", "bin_upper"):
+            out[f"{tag}_ece_{key}"] = np.array([x[key] for x in d["bin_details"]], dtype=np.float64)
+        out[f"{tag}_ece_overall_accuracy"] = np.float64(d["overall_accuracy"])
+        out[f"{tag}_ece_overall_confidence"] = np.float64(d["overall_confidence"])
+        rel = cal.compute_reliability_diagram_data(la, tgt)
+        out[f"{tag}_rel_centers"] = rel["bin_centers"]
+        ens = met.EnsembleDisagreementMetrics()
+        out[f"{tag}_mi"] = ens.compute_disagreement_map([la, lb]).numpy()
+        out[f"{tag}_var"] = ens.compute_variance_map([la, lb]).numpy()
+        out[f"{tag}_js"] = ens.compute_jensen_shannon_divergence(la, lb).numpy()
+        out[f"{tag}_auroc"] = np.float64(ens.compute_disagreement_auroc([la, lb], tgt))
+        rob = met.RobustnessMetrics(num_classes=c)
+        comp = rob.compute_comprehensive_metrics(la, tgt, [la, lb], "fog")
+        out[f"{tag}_comp_keys"] = json.dumps(sorted(comp.keys()))
+        out[f"{tag}_comp_vals"] = np.array([comp[k] for k in sorted(comp.keys())], dtype=np.float64)
+        out[f"{tag}_temp_scaled"] = cal.temperature_scale(la, 1.7).numpy()
+    rob = met.RobustnessMetrics()
+    out["degr"] = np.array([rob.compute_robustness_degradation_ratio(a, b)
+                            for a, b in ((0.5, 0.4), (0.0, 0.3), (0.4, 0.5), (0.78, 0.65))])
+    summ = rob.create_robustness_summary({
+        "clean": {"mean_iou": 0.5, "expected_calibration_error": 0.02, "ensemble_disagreement_auroc": 0.7},
+        "fog": {"mean_iou": 0.3, "expected_calibration_error": 0.05},
+        "night": {"mean_iou": 0.45, "expected_calibration_error": 0.03, "ensemble_disagreement_auroc": 0.6},
+    })
+    out["summary_keys"] = json.dumps(sorted(summ.keys()))
+    out["summary_vals"] = np.array([summ[k] for k in sorted(summ.keys())], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+
+
+def fusion_cases():
+    out = {"versions": versions()}
+    torch.manual_seed(5)
+    b, c, h, w = 2, 19, 24, 40
+    l1 = torch.randn(b, c, h, w) * 2
+    l2 = torch.randn(b, c, h, w) * 2 + 0.5 * l1
+    d1 = torch.rand(b, 1, h, w)
+    d2 = torch.rand(b, 1, h, w)
+    out["l1"], out["l2"], out["d1"], out["d2"] = l1.numpy(), l2.numpy(), d1.numpy(), d2.numpy()
+    raw_w = torch.tensor([0.3, 0.9])
+    temp = torch.tensor([1.7])
+    out["raw_w"], out["temp"] = raw_w.numpy(), temp.numpy()
+    for strat in ("weighted_average", "max_confidence", "mean_anything"):
+        for ts in (True, False):
+            ens = refshim.ensemble_with_fixed_members(l1, l2, strat, ts, raw_w, temp, d1, d2)
+            with torch.no_grad():
+                r = ens(torch.zeros(b, 3, h, w))
+            tag = f"{strat}_{'T' if ts else 'noT'}"
+            out[f"{tag}_seg"] = r["segmentation"].numpy()
+            out[f"{tag}_depth"] = r["depth"].numpy()
+            out[f"{tag}_dis"] = ens.get_ensemble_disagreement(torch.zeros(b, 3, h, w)).numpy()
+    np.savez_compressed(os.path.join(HERE, "fusion.npz"), **out)
+
+
+def loss_cases():
+    m = refshim.model()
+    out = {"versions": versions()}
+    torch.manual_seed(9)
+    b, c, h, w = 2, 19, 24, 40
+    logits = torch.randn(b, c, h, w)
+    depth = torch.rand(b, 1, h, w) * 50
+    label = torch.randint(0, c, (b, h, w))
+    dtgt = torch.rand(b, h, w) * 50
+    fd = torch.rand(b, h, w)
+    out.update(logits=logits.numpy(), depth=depth.numpy(), label=label.numpy(),
+               dtgt=dtgt.numpy(), fd=fd.numpy())
+    variants = {
+        "ce_fd_depth": dict(base="cross_entropy", fd=True, dpred=True, dtgt=True),
+        "ce_fd_nodepth": dict(base="cross_entropy", fd=True, dpred=False, dtgt=False),
+        "ce_nofd_nodepth": dict(base="cross_entropy", fd=False, dpred=False, dtgt=False),
+        "focal_fd_depth": dict(base="focal", fd=True, dpred=True, dtgt=True),
+        "ce_pathB": dict(base="cross_entropy", fd=False, dpred=True, dtgt=True),
+        "ce_fd_dpred_only": dict(base="cross_entropy", fd=True, dpred=True, dtgt=False),
+    }
+    for tag, v in variants.items():
+        lg = logits.clone().requires_grad_(True)
+        dp = depth.clone().requires_grad_(True)
+        pred = {"segmentation": lg}
+        tgt = {"label": label}
+        if v["dpred"]:
+            pred["depth"] = dp
+        if v["dtgt"]:
+            tgt["depth"] = dtgt
+        fn = m.FogDensityAwareLoss(base_loss=v["base"])
+        r = fn(pred, tgt, fd if v["fd"] else None)
+        r["total_loss"].backward()
+        out[f"{tag}_total"] = np.float64(r["total_loss"].item())
+        out[f"{tag}_seg"] = np.float64(r["segmentation_loss"].item())
+        dl = r["depth_loss"]
+        out[f"{tag}_depthloss"] = np.float64(dl.item() if torch.is_tensor(dl) else dl)
+        out[f"{tag}_dlogits"] = lg.grad.numpy()
+        out[f"{tag}_ddepth"] = dp.grad.numpy() if dp.grad is not None else np.zeros(0, np.float32)
+    out["fd_from_depth"] = m.FogDensityAwareLoss()._estimate_fog_density_from_depth(depth.squeeze(1)).numpy()
+    np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
+
+
+if __name__ == "__main__":
+    if not refshim.available():
+        raise SystemExit("reference not present; golden files can only be regenerated in the build container")
+    weather_cases()
+    metric_cases()
+    fusion_cases()
+    loss_cases()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
