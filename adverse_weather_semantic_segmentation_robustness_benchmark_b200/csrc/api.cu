@@ -1,0 +1,48 @@
+// libawx: version, error reporting, device queries.
+#include "awx_internal.cuh"
+
+namespace awx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), where);
+  return (int)e;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    cached = prop.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace awx
+
+extern "C" int awx_version(void) { return AWX_VERSION; }
+
+extern "C" const char* awx_last_error(void) { return awx::g_err; }
+
+extern "C" int awx_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  AWX_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  AWX_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sms) *sms = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return AWX_OK;
+}

@@ -1,0 +1,226 @@
+"""Tensor-level wrappers over the C ABI (include/awx.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every function below
+passes raw ``data_ptr()``s to libawx.so.  Nothing falls back to torch arithmetic.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LN2 = math.log(2.0)
+DEFAULT_AUROC_BINS = 4096
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "adverse_weather_semantic_segmentation_robustness_benchmark_b200 needs a CUDA device: "
+            "its arithmetic lives in libawx.so (sm_100a) and there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Contiguous CUDA copy/view of `t` (host tensors are uploaded)."""
+    dev = require_cuda()
+    if not t.is_cuda:
+        t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def label_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.uint8:
+        return _lib.LABEL_U8
+    if t.dtype == torch.int64:
+        return _lib.LABEL_I64
+    raise TypeError(f"labels must be uint8 or int64, got {t.dtype}")
+
+
+def normalise_labels(t: torch.Tensor) -> torch.Tensor:
+    """uint8 stays uint8 (the reference's wrap quirk depends on it); every other integer type is
+    widened to int64, which is what torch's promotion does in the reference's expressions."""
+    if t.dtype in (torch.uint8, torch.int64):
+        return to_device(t)
+    if t.dtype in (torch.int8, torch.int16, torch.int32, torch.bool):
+        return to_device(t, torch.int64)
+    raise TypeError(f"labels must be an integer tensor, got {t.dtype}")
+
+
+def ece_edges(num_bins: int) -> torch.Tensor:
+    """Bin boundaries exactly as the reference builds them (evaluation/metrics.py:179)."""
+    return torch.linspace(0, 1, num_bins + 1)
+
+
+@dataclass
+class Bins:
+    """Host view of the int64 bins buffer (layout: include/awx.h, AwxBinsLayout)."""
+    raw: np.ndarray
+    num_classes: int
+    ece_bins: int
+    auroc_bins: int
+
+    def __post_init__(self):
+        self.layout = _lib.bins_layout(self.num_classes, self.ece_bins, self.auroc_bins)
+
+    def _seg(self, off, n):
+        return self.raw[off:off + n]
+
+    @property
+    def confusion(self) -> np.ndarray:
+        c = self.num_classes
+        return self._seg(self.layout.confusion, c * c).reshape(c, c)
+
+    @property
+    def ece_count(self):
+        return self._seg(self.layout.ece_count, self.ece_bins)
+
+    @property
+    def ece_correct(self):
+        return self._seg(self.layout.ece_correct, self.ece_bins)
+
+    @property
+    def ece_conf_sum(self) -> np.ndarray:
+        """Per-bin sum of confidences (float64), from the 2^-31 fixed-point words."""
+        hi = self._seg(self.layout.ece_conf_hi, self.ece_bins)
+        lo = self._seg(self.layout.ece_conf_lo, self.ece_bins)
+        return np.array([(int(h) * (1 << 32) + int(l)) / float(1 << 31) for h, l in zip(hi, lo)], dtype=np.float64)
+
+    @property
+    def auroc_pos(self):
+        return self._seg(self.layout.auroc_pos, self.auroc_bins)
+
+    @property
+    def auroc_neg(self):
+        return self._seg(self.layout.auroc_neg, self.auroc_bins)
+
+    def counter(self, which: int) -> int:
+        return int(self.raw[self.layout.counters + which])
+
+
+def new_bins(num_classes: int, ece_bins: int = 15, auroc_bins: int = 0) -> torch.Tensor:
+    lay = _lib.bins_layout(num_classes, ece_bins, auroc_bins)
+    return torch.zeros(lay.total_words, dtype=torch.int64, device=require_cuda())
+
+
+def score(logits_a: torch.Tensor, logits_b: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, *,
+          strategy: int = _lib.FUSE_SINGLE, w0: float = 0.5, w1: float = 0.5,
+          temperature: Optional[float] = None, ignore_index: int = 255,
+          ece_bins: int = 15, auroc_bins: int = 0, auroc_hi: float = LN2,
+          bins: Optional[torch.Tensor] = None,
+          want_pred: Optional[torch.dtype] = None, want_fused: bool = False, want_conf: bool = False,
+          want_mi: bool = False, want_js: bool = False) -> dict:
+    """One fused pass over [B,C,H,W] fp32 logits (one or two members).  Returns a dict with
+    ``bins`` (device int64 buffer, accumulated into if given) and the requested maps."""
+    lib = _lib.load()
+    a = to_device(logits_a, torch.float32)
+    if a.dim() != 4:
+        raise ValueError(f"logits must be [B,C,H,W], got shape {tuple(a.shape)}")
+    bsz, ncls, h, w = a.shape
+    ens = strategy != _lib.FUSE_SINGLE
+    b = None
+    if ens:
+        if logits_b is None:
+            raise ValueError("an ensemble strategy needs two members")
+        b = to_device(logits_b, torch.float32)
+        if b.shape != a.shape:
+            raise ValueError(f"member shapes differ: {tuple(a.shape)} vs {tuple(b.shape)}")
+    lab = None
+    if labels is not None:
+        lab = normalise_labels(labels)
+        if lab.numel() != bsz * h * w:
+            raise ValueError(f"labels have {lab.numel()} elements, expected {bsz * h * w}")
+    nb_auroc = auroc_bins if ens else 0
+    cfg = _lib.ScoreConfig()
+    cfg.num_classes, cfg.strategy = ncls, strategy
+    cfg.w0, cfg.w1 = float(w0), float(w1)
+    cfg.use_temperature = 0 if temperature is None else 1
+    cfg.temperature = 1.0 if temperature is None else float(temperature)
+    cfg.label_dtype = _lib.LABEL_I64 if lab is None else label_code(lab)
+    cfg.ignore_index = ignore_index
+    cfg.ece_bins, cfg.auroc_bins, cfg.auroc_hi = ece_bins, nb_auroc, float(auroc_hi)
+    edges = ece_edges(ece_bins).numpy()
+    for i, e in enumerate(edges):
+        cfg.ece_edges[i] = float(e)
+    dev = a.device
+    out = {}
+    if lab is not None:
+        if bins is None:
+            bins = new_bins(ncls, ece_bins, nb_auroc)
+        out["bins"] = bins
+    maps = _lib.ScoreMaps()
+    if want_pred is not None:
+        if want_pred not in (torch.uint8, torch.int64):
+            raise TypeError("want_pred must be torch.uint8 or torch.int64")
+        out["pred"] = torch.empty((bsz, h, w), dtype=want_pred, device=dev)
+        maps.pred = out["pred"].data_ptr()
+        maps.pred_dtype = _lib.PRED_U8 if want_pred == torch.uint8 else _lib.PRED_I64
+    if want_fused:
+        out["fused"] = torch.empty_like(a)
+        maps.fused = out["fused"].data_ptr()
+    if want_conf:
+        out["conf"] = torch.empty((bsz, h, w), dtype=torch.float32, device=dev)
+        maps.conf = out["conf"].data_ptr()
+    if want_mi and ens:
+        out["mi"] = torch.empty((bsz, h, w), dtype=torch.float32, device=dev)
+        maps.mi = out["mi"].data_ptr()
+    if want_js and ens:
+        out["js"] = torch.empty((bsz, h, w), dtype=torch.float32, device=dev)
+        maps.js = out["js"].data_ptr()
+    rc = lib.awx_score(_ptr(a), _ptr(b), _ptr(lab), bsz, h * w, C.byref(cfg),
+                       _ptr(bins) if lab is not None else None, C.byref(maps), _stream())
+    _lib.check(rc, "awx_score")
+    return out
+
+
+def read_bins(bins: torch.Tensor, num_classes: int, ece_bins: int = 15, auroc_bins: int = 0) -> Bins:
+    """Device -> host read of a bins buffer (synchronises the current stream)."""
+    return Bins(bins.cpu().numpy(), num_classes, ece_bins, auroc_bins)
+
+
+def member_variance(logits_a: torch.Tensor, logits_b: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    a = to_device(logits_a, torch.float32)
+    b = to_device(logits_b, torch.float32)
+    if a.shape != b.shape or a.dim() != 4:
+        raise ValueError("member_variance needs two [B,C,H,W] tensors of equal shape")
+    out = torch.empty_like(a)
+    bsz, ncls, h, w = a.shape
+    _lib.check(lib.awx_member_variance(_ptr(a), _ptr(b), _ptr(out), bsz, ncls, h * w, _stream()), "awx_member_variance")
+    return out
+
+
+def confusion(pred: torch.Tensor, labels: torch.Tensor, num_classes: int, ignore_index: int = 255):
+    """(confusion int64 [C,C] device tensor, counters int64 [8] device tensor) from prediction maps."""
+    lib = _lib.load()
+    lab = normalise_labels(labels).reshape(-1)
+    if pred.dtype not in (torch.uint8, torch.int64):
+        pred = pred.to(torch.int64)
+    prd = to_device(pred).reshape(-1)
+    if prd.numel() != lab.numel():
+        raise ValueError(f"predictions ({prd.numel()}) and targets ({lab.numel()}) differ in size")
+    dev = require_cuda()
+    cm = torch.zeros(num_classes * num_classes, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+    rc = lib.awx_confusion(_ptr(prd), _lib.PRED_U8 if prd.dtype == torch.uint8 else _lib.PRED_I64,
+                           _ptr(lab), label_code(lab), prd.numel(), num_classes, ignore_index,
+                           _ptr(cm), _ptr(cnt), _stream())
+    _lib.check(rc, "awx_confusion")
+    return cm.view(num_classes, num_classes), cnt

@@ -1,0 +1,205 @@
+/*
+ * awx.h -- C ABI of libawx.so, the B200 (sm_100a) implementation of the
+ * adverse-weather robustness-evaluation hot path.
+ *
+ * The reference (A-SHOJAEI/adverse-weather-semantic-segmentation-robustness-benchmark)
+ * is pure Python and has no FFI of its own; its boundary for this path is its public
+ * class API.  Each entry point below therefore names the reference method(s) whose
+ * per-pixel arithmetic it replaces (paths relative to
+ * src/adverse_weather_semantic_segmentation_robustness_benchmark/).  INTEGRATION.md
+ * shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every data pointer is a DEVICE pointer unless its comment says HOST.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
+ *   - kernels never allocate: the caller owns inputs, outputs, bins and workspaces.
+ *   - return value: 0 = ok; <0 = argument error (AWX_E_*); >0 = cudaError_t.
+ *     awx_last_error() returns the thread-local message of the last failure.
+ *   - there is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef AWX_H_
+#define AWX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AWX_VERSION 100 /* major*100 + minor */
+
+#define AWX_OK 0
+#define AWX_E_ARG (-1)         /* null / negative / inconsistent argument       */
+#define AWX_E_UNSUPPORTED (-2) /* e.g. num_classes > AWX_MAX_CLASSES            */
+#define AWX_E_ALIGN (-3)       /* pointer not aligned as documented             */
+
+#define AWX_MAX_CLASSES 64
+#define AWX_MAX_ECE_BINS 64
+#define AWX_MAX_AUROC_BINS 8192
+
+int awx_version(void);
+const char* awx_last_error(void);
+/* SM count / compute capability of the current device (for grid sizing by callers). */
+int awx_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * Scoring: fuse -> softmax -> argmax -> confusion / ECE / AUROC bins, one pass over HBM.
+ *
+ * Replaces the per-pixel arithmetic of
+ *   EnsembleModel.forward fusion            models/model.py:442-462
+ *   EnsembleModel.get_ensemble_disagreement models/model.py:498-513
+ *   IoUMetrics.compute_iou / compute_pixel_accuracy   evaluation/metrics.py:34-123
+ *   ConfidenceCalibration.compute_ece                 evaluation/metrics.py:143-226
+ *   EnsembleDisagreementMetrics.compute_disagreement_map / _auroc / _jensen_shannon_divergence
+ *                                                     evaluation/metrics.py:336-369, 393-467
+ * ---------------------------------------------------------------------------------- */
+
+enum {
+  AWX_FUSE_SINGLE = 0,   /* one member: logits_b ignored                                    */
+  AWX_FUSE_WEIGHTED = 1, /* w0*a + w1*b, three separately rounded fp32 ops (model.py:445)   */
+  AWX_FUSE_MAXCONF = 2,  /* member with the larger max-softmax, strict > (model.py:449-455) */
+  AWX_FUSE_MEAN = 3      /* (a + b) / 2 (model.py:457)                                      */
+};
+
+enum {
+  AWX_LABEL_U8 = 0, /* uint8 labels; confusion index (t*C mod 256)+pred, the reference's
+                       uint8 wrap (metrics.py:68)                              */
+  AWX_LABEL_I64 = 1 /* int64 labels; index t*C+pred                                       */
+};
+
+enum { AWX_PRED_U8 = 0, AWX_PRED_I64 = 1 };
+
+typedef struct AwxScoreConfig {
+  int32_t num_classes;     /* C, 1..AWX_MAX_CLASSES (C == 19 has a register-resident kernel) */
+  int32_t strategy;        /* AWX_FUSE_*                                                     */
+  float w0, w1;            /* softmax(ensemble_weights) computed by the host in fp32         */
+  float temperature;       /* divisor of the fused logits                                    */
+  int32_t use_temperature; /* 0: no division (temperature_scaling=False)                     */
+  int32_t label_dtype;     /* AWX_LABEL_*                                                    */
+  int32_t ignore_index;    /* 255                                                            */
+  int32_t ece_bins;        /* 1..AWX_MAX_ECE_BINS                                            */
+  int32_t auroc_bins;      /* 0 = no AUROC histogram; else 1..AWX_MAX_AUROC_BINS             */
+  float auroc_hi;          /* MI histogram covers [0, auroc_hi) linearly (ln 2 for 2 members)*/
+  float ece_edges[AWX_MAX_ECE_BINS + 1]; /* torch.linspace(0,1,bins+1) as fp32, from the host */
+} AwxScoreConfig;
+
+/* Optional per-pixel outputs; any pointer may be NULL. */
+typedef struct AwxScoreMaps {
+  void* pred;         /* [B,HW] argmax of the fused (temperature-scaled) logits            */
+  int32_t pred_dtype; /* AWX_PRED_*                                                        */
+  int32_t reserved;
+  float* fused; /* [B,C,HW] fused logits, bit-exact (true fp32 division by temperature)    */
+  float* conf;  /* [B,HW] max softmax probability of the fused logits                      */
+  float* mi;    /* [B,HW] mutual-information disagreement (metrics.py:358-367)             */
+  float* js;    /* [B,HW] 0.5*[KL(m||p)+KL(m||q)] (model.py:505-511)                       */
+} AwxScoreMaps;
+
+/* Word offsets into the int64 `bins` buffer (all counts; summing buffers of several
+ * ranks/launches with a plain integer add is exact and order-independent).
+ *   confusion  [C*C]      rows = target, cols = prediction
+ *   ece_count  [nb]       pixels with edges[b] < conf <= edges[b+1]
+ *   ece_correct[nb]       of those, pred == target
+ *   ece_conf_hi[nb], ece_conf_lo[nb]   sum of conf in 2^-31 fixed point = hi*2^32 + lo
+ *   auroc_pos  [NB], auroc_neg[NB]     MI histogram of wrong / right ensemble pixels
+ *   counters   [8]        AWX_CNT_*                                                   */
+typedef struct AwxBinsLayout {
+  int64_t confusion, ece_count, ece_correct, ece_conf_hi, ece_conf_lo;
+  int64_t auroc_pos, auroc_neg, counters, total_words;
+} AwxBinsLayout;
+
+enum {
+  AWX_CNT_VALID = 0,     /* label != ignore_index                                          */
+  AWX_CNT_CORRECT = 1,   /* valid and argmax(fused) == label                               */
+  AWX_CNT_BAD_LABEL = 2, /* valid but confusion index outside [0,C*C): reference raises    */
+  AWX_CNT_ECE_AMBIG = 3, /* valid pixels whose confidence is within 3 fp32 ulp of an
+                            interior bin edge (the reference's own rounding noise)          */
+  AWX_CNT_ENS_WRONG = 4, /* valid and argmax(mean member prob) != label (AUROC positives)  */
+  AWX_CNT_PICK_AMBIG = 5,/* MAXCONF: member confidences within 4 ulp of each other         */
+  AWX_CNT_NO_BIN = 6,    /* valid pixels whose confidence fell in no bin (0, NaN)          */
+  AWX_CNT_PIXELS = 7     /* all pixels seen                                                */
+};
+
+int awx_bins_layout(int32_t num_classes, int32_t ece_bins, int32_t auroc_bins, AwxBinsLayout* out /*HOST*/);
+
+/* logits_a/logits_b: fp32 [B,C,HW] contiguous (NCHW with HW = H*W).  labels: [B,HW] of
+ * cfg->label_dtype, or NULL (then no bins are touched and `bins` may be NULL).
+ * `bins` must be zeroed by the caller before the first call; calls accumulate. */
+int awx_score(const float* logits_a, const float* logits_b, const void* labels,
+              int64_t batch, int64_t pixels_per_image, const AwxScoreConfig* cfg /*HOST*/,
+              int64_t* bins, const AwxScoreMaps* maps /*HOST, may be NULL*/, void* stream);
+
+/* Confusion matrix from a prediction map (IoUMetrics.compute_iou / compute_pixel_accuracy with
+ * [B,H,W] predictions, evaluation/metrics.py:53-71, 110-123).  pred: AWX_PRED_* dtype, labels:
+ * AWX_LABEL_* dtype, n elements each.  The index is formed with torch's type promotion:
+ * uint8*C wraps mod 256, and uint8 labels + uint8 predictions wrap as a whole.
+ * confusion: int64 [C*C]; counters: int64 [8] (AWX_CNT_VALID / _CORRECT / _BAD_LABEL / _PIXELS). */
+int awx_confusion(const void* pred, int32_t pred_dtype, const void* labels, int32_t label_dtype, int64_t n,
+                  int32_t num_classes, int32_t ignore_index, int64_t* confusion, int64_t* counters, void* stream);
+
+/* Unbiased variance over the two members of the class probabilities, [B,C,HW]
+ * (EnsembleDisagreementMetrics.compute_variance_map, evaluation/metrics.py:384-391). */
+int awx_member_variance(const float* logits_a, const float* logits_b, float* out,
+                        int64_t batch, int32_t num_classes, int64_t pixels_per_image, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Weather corruption (WeatherDegradationTransforms, data/preprocessing.py:61-248).
+ * Stochastic parameters are drawn on the host with the reference's RNG and passed in.
+ * ---------------------------------------------------------------------------------- */
+
+enum { AWX_CLEAN = 0, AWX_FOG = 1, AWX_RAIN = 2, AWX_SNOW = 3, AWX_NIGHT = 4 };
+enum { AWX_F32 = 0, AWX_F64 = 1 };
+
+/* One per image (device array).  Field/overlay offsets are in ELEMENTS of the arrays
+ * passed to awx_corrupt. */
+typedef struct AwxCorruptParams {
+  int32_t kind;        /* AWX_CLEAN..AWX_NIGHT                                              */
+  int32_t blur_k;      /* rain: 3; snow: 3 or 7                                             */
+  double d0;           /* fog: beta            night: intensity (noise*intensity*0.5, fp64) */
+  double d1;           /* fog: airlight A                                                   */
+  float f0;            /* rain: fp32(1-haze)   snow: fp32(0.2*I)   night: fp32(1 - I*u)     */
+  float f1;            /* rain: fp32(haze*0.7)                                              */
+  float taps[4];       /* rain/snow: half Gaussian kernel, taps[0] = centre                 */
+  int64_t field_offset;/* fog: depth[H*W]; night: noise[H*W*3]; element offset into `field` */
+  int32_t item_begin;  /* rain: drops; snow: flakes -- range into `items`                   */
+  int32_t item_count;
+} AwxCorruptParams;
+
+/* items: int32 [n,5].  rain: x0,y0,x1,y1,thickness (cv2.line, preprocessing.py:160);
+ * snow: x,y,radius,0,0 (cv2.circle filled, :194).
+ * field: depth (fog, :227-248 output) or Gaussian noise (night, :222), fp32 or fp64.
+ * mask_ws: workspace of awx_corrupt_workspace_bytes() bytes, needed only when a rain or snow
+ * image is present; the call clears and fills it itself.
+ * img / out: uint8 [B,H,W,3]; `out` of an AWX_CLEAN image is a copy of `img`. */
+size_t awx_corrupt_workspace_bytes(int64_t batch, int32_t height, int32_t width);
+
+int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int32_t height, int32_t width,
+                const AwxCorruptParams* params, const void* field, int32_t field_dtype,
+                const int32_t* items, int64_t n_items, void* mask_ws, void* stream);
+
+/* depth = max(gaussian_filter(ramp + noise, sigma=2, reflect), 1) in fp64
+ * (_generate_synthetic_depth, preprocessing.py:235-246).  noise: fp64 [B,H,W] drawn by the
+ * host; out: fp64 or fp32 [B,H,W]; tmp: fp64 [B,H,W] workspace. */
+int awx_synth_depth(const double* noise, void* out, int32_t out_dtype, double* tmp,
+                    int64_t batch, int32_t height, int32_t width, double depth_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fog-density-aware loss, forward + unscaled gradients in one pass
+ * (FogDensityAwareLoss.forward, models/model.py:560-617; focal :619-642).
+ * sums[0] = sum_i w_i * loss_i, sums[1] = sum_i (depth_pred-depth_tgt)^2 (fp64, device).
+ * dlogits (nullable) = w_i * dloss_i/dlogit / N ; ddepth (nullable) = 2*(pred-tgt)/N.
+ * ---------------------------------------------------------------------------------- */
+int awx_fogloss(const float* logits, const void* labels, int32_t label_dtype,
+                const float* fog_density /*nullable*/, const float* depth_pred /*nullable*/,
+                const float* depth_tgt /*nullable*/, float fog_sensitivity, int32_t focal,
+                int64_t batch, int32_t num_classes, int64_t pixels_per_image,
+                double* sums, float* dlogits, float* ddepth, int64_t* bad_labels, void* stream);
+
+/* x[i] *= *scale (device scalar) -- backward of a mean-reduced loss with grad_output != 1. */
+int awx_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWX_H_ */
