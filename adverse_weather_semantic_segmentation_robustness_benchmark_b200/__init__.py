@@ -15,7 +15,13 @@ from .evaluation.metrics import (  # noqa: F401
     RobustnessMetrics,
 )
 
+from .data.preprocessing import WeatherDegradationTransforms  # noqa: F401,E402
+from .models.model import EnsembleModel, FogDensityAwareLoss  # noqa: F401,E402
+
 __all__ = [
+    "WeatherDegradationTransforms",
+    "EnsembleModel",
+    "FogDensityAwareLoss",
     "IoUMetrics",
     "ConfidenceCalibration",
     "EnsembleDisagreementMetrics",

@@ -78,10 +78,11 @@ _SIGNATURES = {
     "awx_corrupt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                               C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "awx_synth_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
-                                  C.c_double, C.c_void_p]),
+                                  C.c_double, C.c_void_p, C.c_int32, C.c_void_p]),
     "awx_fogloss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                               C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                              C.c_void_p, C.c_void_p]),
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "awx_fogloss_workspace_bytes": (C.c_size_t, []),
     "awx_scale_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

@@ -1,0 +1,417 @@
+// awx_corrupt: fog / rain / snow / night weather corruption of uint8 HWC frames (and clean copy).
+//
+// Three kernels, chosen per image by AwxCorruptParams.kind:
+//   rasterize_kernel  streaks (cv2.line) and flakes (cv2.circle) -> 1 bit/pixel overlay mask
+//   pointwise_kernel  clean / fog / night: 1024-pixel chunks staged through shared memory so that
+//                     global traffic is 128-bit and coalesced although a pixel is 3 bytes
+//   blur_kernel<R>    rain / snow: 16x128 pixel tiles (+R halo, BORDER_REFLECT_101) in shared
+//                     memory: point op + overlay -> horizontal pass -> vertical pass -> uint8
+//
+// Arithmetic mirrors the reference's dtype promotions (data/preprocessing.py):
+//   u8 -> fp32 by a true division by 255 (256-entry table built with __fdiv_rn)        :81
+//   fog:   fp64, separately rounded ops; airlight is rounded to fp32 first (A*ones_like) :117-123
+//   night: fp32 dim + colour shift, then fp64 noise add                                 :213-225
+//   rain / snow: fp32 throughout, OpenCV-style separable Gaussian                       :135-168, :180-202
+//   final: clip to [0,1], times 255, truncate toward zero
+#include "awx_internal.cuh"
+#include "raster.cuh"
+
+namespace awx {
+namespace {
+
+constexpr int kChunkPx = 1024;          // pointwise: pixels per chunk (3072 B = 192 x 16 B)
+constexpr int kPointThreads = 256;
+constexpr int kTileW = 128, kTileH = 16;  // blur tile
+constexpr int kBlurThreads = 256;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  // BORDER_REFLECT_101: gfedcb|abcdefgh|gfedcba
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
+  return i;
+}
+
+__device__ __forceinline__ void build_unit_table(float* lut) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
+}
+
+__device__ __forceinline__ unsigned to_u8_f64(double v) {
+  v = fmin(fmax(v, 0.0), 1.0);
+  return (unsigned)__double2int_rz(__dmul_rn(v, 255.0));
+}
+__device__ __forceinline__ unsigned to_u8_f32(float v) {
+  v = fminf(fmaxf(v, 0.0f), 1.0f);
+  return (unsigned)__float2int_rz(__fmul_rn(v, 255.0f));
+}
+
+// -------------------------------------------------------------------------- overlay mask
+__global__ void __launch_bounds__(128) rasterize_kernel(const AwxCorruptParams* __restrict__ params,
+                                                         const int32_t* __restrict__ items, unsigned* __restrict__ mask,
+                                                         int H, int W, int WW) {
+  const int b = blockIdx.y;
+  const AwxCorruptParams prm = params[b];
+  if (prm.kind != AWX_RAIN && prm.kind != AWX_SNOW) return;
+  unsigned* m = mask + (size_t)b * H * WW;
+  auto emit = [&](int y, int x0, int x1) {
+    unsigned* row = m + (size_t)y * WW;
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    for (int wd = w0; wd <= w1; ++wd) {
+      const int lo = wd == w0 ? (x0 & 31) : 0;
+      const int hi = wd == w1 ? (x1 & 31) : 31;
+      const unsigned bits = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+      atomicOr(row + wd, bits);
+    }
+  };
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < prm.item_count; i += gridDim.x * blockDim.x) {
+    const int32_t* it = items + 5 * (size_t)(prm.item_begin + i);
+    if (prm.kind == AWX_RAIN)
+      raster::line(it[0], it[1], it[2], it[3], it[4], W, H, emit);
+    else
+      raster::disc(it[0], it[1], it[2], W, H, emit);
+  }
+}
+
+// ------------------------------------------------------------------- clean / fog / night
+template <typename FT>
+__global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t* __restrict__ img,
+                                                                   uint8_t* __restrict__ out,
+                                                                   const AwxCorruptParams* __restrict__ params,
+                                                                   const FT* __restrict__ field, long long HW) {
+  const int b = blockIdx.y;
+  const AwxCorruptParams prm = params[b];
+  if (prm.kind != AWX_CLEAN && prm.kind != AWX_FOG && prm.kind != AWX_NIGHT) return;
+  __shared__ __align__(16) unsigned s_in[kChunkPx * 3 / 4];
+  __shared__ __align__(16) unsigned s_out[kChunkPx * 3 / 4];
+  __shared__ float s_unit[256];
+  build_unit_table(s_unit);
+  const uint8_t* src = img + (size_t)b * HW * 3;
+  uint8_t* dst = out + (size_t)b * HW * 3;
+  const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+  const long long nchunks = (HW + kChunkPx - 1) / kChunkPx;
+  const FT* fld = field ? field + prm.field_offset : nullptr;
+  const double neg_beta = -prm.d0;  // numpy evaluates (-beta) * depth
+  const double airlight = prm.d1;   // already rounded to fp32 by the host (A * ones_like(fp32))
+  const float gain = prm.f0;
+  const double night_i = prm.d0;
+
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long px0 = ch * kChunkPx;
+    const int npx = (int)((HW - px0) < kChunkPx ? (HW - px0) : kChunkPx);
+    const bool full = aligned && npx == kChunkPx;
+    __syncthreads();  // previous iteration's stores have left s_out; table is ready
+    if (full) {
+      if (threadIdx.x < kChunkPx * 3 / 16)
+        reinterpret_cast<uint4*>(s_in)[threadIdx.x] = ld_stream_u4(src + px0 * 3 + threadIdx.x * 16);
+    } else {
+      uint8_t* sb = reinterpret_cast<uint8_t*>(s_in);
+      for (int i = threadIdx.x; i < npx * 3; i += kPointThreads) sb[i] = src[px0 * 3 + i];
+    }
+    __syncthreads();
+    const int p = threadIdx.x * 4;  // 4 pixels = 12 bytes = 3 words; bank = 3*t mod 32: conflict free
+    if (p < npx) {
+      unsigned wv[3] = {s_in[threadIdx.x * 3], s_in[threadIdx.x * 3 + 1], s_in[threadIdx.x * 3 + 2]};
+      if (prm.kind != AWX_CLEAN) {
+        unsigned ov[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool live = p + j < npx;
+          double tr = 0.0, veil = 0.0;
+          if (prm.kind == AWX_FOG) {
+            const double d = live ? (double)fld[px0 + p + j] : 1.0;
+            tr = exp(__dmul_rn(neg_beta, d));
+            veil = __dmul_rn(airlight, __dsub_rn(1.0, tr));
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int k = j * 3 + c;  // byte index within the 12
+            const unsigned u = (wv[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+            const float x = s_unit[u];
+            unsigned r;
+            if (prm.kind == AWX_FOG) {
+              r = to_u8_f64(__dadd_rn(__dmul_rn((double)x, tr), veil));
+            } else {  // night
+              const float shift = c == 0 ? 0.8f : (c == 1 ? 0.85f : 1.2f);
+              const float v = __fmul_rn(__fmul_rn(x, gain), shift);
+              const double nz = live ? (double)fld[(px0 + p + j) * 3 + c] : 0.0;
+              r = to_u8_f64(__dadd_rn((double)v, __dmul_rn(__dmul_rn(nz, night_i), 0.5)));
+            }
+            ov[k >> 2] |= r << ((k & 3) * 8);
+          }
+        }
+        wv[0] = ov[0];
+        wv[1] = ov[1];
+        wv[2] = ov[2];
+      }
+      s_out[threadIdx.x * 3] = wv[0];
+      s_out[threadIdx.x * 3 + 1] = wv[1];
+      s_out[threadIdx.x * 3 + 2] = wv[2];
+    }
+    __syncthreads();
+    if (full) {
+      if (threadIdx.x < kChunkPx * 3 / 16)
+        st_stream_u4(dst + px0 * 3 + threadIdx.x * 16, reinterpret_cast<const uint4*>(s_out)[threadIdx.x]);
+    } else {
+      const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_out);
+      for (int i = threadIdx.x; i < npx * 3; i += kPointThreads) dst[px0 * 3 + i] = sb[i];
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- rain / snow
+template <int R>
+__global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
+                                                             const AwxCorruptParams* __restrict__ params,
+                                                             const unsigned* __restrict__ mask, int H, int W, int WW) {
+  constexpr int PW = kTileW + 2 * R;  // haloed tile width in pixels
+  constexpr int PH = kTileH + 2 * R;
+  constexpr int PRE_STRIDE = PW * 3;
+  constexpr int ROW = kTileW * 3;
+  const int b = blockIdx.z;
+  const AwxCorruptParams prm = params[b];
+  if ((prm.kind != AWX_RAIN && prm.kind != AWX_SNOW) || prm.blur_k != 2 * R + 1) return;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* s_pre = reinterpret_cast<float*>(smem);      // [PH][PW*3] point-op'ed, overlaid, fp32
+  float* s_h = s_pre + PH * PRE_STRIDE;               // [PH][kTileW*3] after the horizontal pass
+  uint8_t* s_o = reinterpret_cast<uint8_t*>(s_h + PH * ROW);  // [kTileH][kTileW*3]
+  __shared__ float s_unit[256];
+  build_unit_table(s_unit);
+  __syncthreads();
+
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const uint8_t* src = img + (size_t)b * H * W * 3;
+  uint8_t* dst = out + (size_t)b * H * W * 3;
+  const unsigned* m = mask + (size_t)b * H * WW;
+  const bool rain = prm.kind == AWX_RAIN;
+  const float k1 = prm.f0, k2 = prm.f1;  // rain: x*k1 + k2 ; snow: clip(x + k1)
+
+  // ---- stage 1: load (reflect-101), point op, overlay -> s_pre
+  for (int i = threadIdx.x; i < PH * PW; i += kBlurThreads) {
+    const int ry = i / PW, rx = i - ry * PW;
+    const int sy = reflect101(y0 + ry - R, H);
+    const int sx = reflect101(x0 + rx - R, W);
+    const bool over = (m[(size_t)sy * WW + (sx >> 5)] >> (sx & 31)) & 1u;
+    const uint8_t* px = src + ((size_t)sy * W + sx) * 3;
+    float* o = s_pre + ry * PRE_STRIDE + rx * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = s_unit[px[c]];
+      float v;
+      if (rain) {
+        v = __fadd_rn(__fmul_rn(x, k1), k2);
+        if (over) v = c == 0 ? 0.8f : (c == 1 ? 0.9f : 1.0f);
+      } else {
+        v = fminf(fmaxf(__fadd_rn(x, k1), 0.0f), 1.0f);
+        if (over) v = 1.0f;
+      }
+      o[c] = v;
+    }
+  }
+  __syncthreads();
+  // ---- stage 2: horizontal pass
+  const float t0 = prm.taps[0], t1 = prm.taps[1], t2 = prm.taps[2], t3 = prm.taps[3];
+  for (int i = threadIdx.x; i < PH * ROW; i += kBlurThreads) {
+    const int ry = i / ROW, col = i - ry * ROW;
+    const float* p = s_pre + ry * PRE_STRIDE + col + 3 * R;
+    float v;
+    if (R == 1) {
+      v = p[0] * t0 + (p[-3] + p[3]) * t1;
+    } else {
+      // generic row filter order: leftmost tap first
+      v = p[-9] * t3;
+      v += p[-6] * t2;
+      v += p[-3] * t1;
+      v += p[0] * t0;
+      v += p[3] * t1;
+      v += p[6] * t2;
+      v += p[9] * t3;
+    }
+    s_h[i] = v;
+  }
+  __syncthreads();
+  // ---- stage 3: vertical pass (symmetric pairing), clip, scale, truncate
+  for (int i = threadIdx.x; i < kTileH * ROW; i += kBlurThreads) {
+    const int ry = i / ROW, col = i - ry * ROW;
+    const float* p = s_h + (ry + R) * ROW + col;
+    float v = p[0] * t0 + (p[-ROW] + p[ROW]) * t1;
+    if (R == 3) {
+      v += (p[-2 * ROW] + p[2 * ROW]) * t2;
+      v += (p[-3 * ROW] + p[3 * ROW]) * t3;
+    }
+    s_o[i] = (uint8_t)to_u8_f32(v);
+  }
+  __syncthreads();
+  // ---- stage 4: store
+  const int tw = min(kTileW, W - x0), th = min(kTileH, H - y0);
+  const bool vec = tw == kTileW && (((uintptr_t)(dst + ((size_t)y0 * W + x0) * 3)) & 15) == 0 && ((W * 3) & 15) == 0;
+  if (vec) {
+    for (int i = threadIdx.x; i < th * (ROW / 16); i += kBlurThreads) {
+      const int ry = i / (ROW / 16), q = i - ry * (ROW / 16);
+      st_stream_u4(dst + ((size_t)(y0 + ry) * W + x0) * 3 + q * 16, reinterpret_cast<const uint4*>(s_o + ry * ROW)[q]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < th * tw * 3; i += kBlurThreads) {
+      const int ry = i / (tw * 3), col = i - ry * (tw * 3);
+      dst[((size_t)(y0 + ry) * W + x0) * 3 + col] = s_o[ry * ROW + col];
+    }
+  }
+}
+
+template <int R>
+constexpr size_t blur_smem() {
+  return (size_t)(kTileH + 2 * R) * ((kTileW + 2 * R) * 3 + kTileW * 3) * sizeof(float) + (size_t)kTileH * kTileW * 3;
+}
+
+template <int R>
+int launch_blur(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparams, const unsigned* mask, int64_t B, int H,
+                int W, int WW, cudaStream_t s) {
+  auto kern = blur_kernel<R>;
+  AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem<R>()));
+  dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, (unsigned)B);
+  kern<<<grid, kBlurThreads, blur_smem<R>(), s>>>(img, out, dparams, mask, H, W, WW);
+  AWX_CUDA(cudaGetLastError());
+  return AWX_OK;
+}
+
+size_t params_bytes(int64_t B) { return ((size_t)B * sizeof(AwxCorruptParams) + 255) & ~(size_t)255; }
+
+// ------------------------------------------------------------------------ synthetic depth
+// scipy.ndimage.gaussian_filter: correlate1d along axis 0 then axis 1, mode='reflect' (edge
+// sample repeated), symmetric accumulation x0*w0 + sum_{j=-r..-1} (x[j] + x[-j]) * w[j], fp64.
+__device__ __forceinline__ int reflect_dup(int i, int n) {
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - 1 - i;
+  return i;
+}
+
+struct GaussTaps {
+  double w[33];  // w[0] = centre, w[j] = tap at distance j
+  int radius;
+};
+
+template <bool VERTICAL, typename OT>
+__global__ void __launch_bounds__(256) depth_pass_kernel(const double* __restrict__ in, OT* __restrict__ out, int H, int W,
+                                                          long long total, const GaussTaps taps, double scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const long long t = i / W;
+    const int y = (int)(t % H);
+    const double* plane = in + (t / H) * (long long)H * W;
+    auto sample = [&](int yy, int xx) -> double {
+      const double v = plane[(long long)yy * W + xx];
+      // first pass reads noise and adds the vertical ramp (y/H)*scale on the fly
+      return VERTICAL ? __dadd_rn(__dmul_rn(__ddiv_rn((double)yy, (double)H), scale), v) : v;
+    };
+    double acc = __dmul_rn(VERTICAL ? sample(y, x) : sample(y, x), taps.w[0]);
+    for (int j = taps.radius; j >= 1; --j) {
+      double lo, hi;
+      if (VERTICAL) {
+        lo = sample(reflect_dup(y - j, H), x);
+        hi = sample(reflect_dup(y + j, H), x);
+      } else {
+        lo = sample(y, reflect_dup(x - j, W));
+        hi = sample(y, reflect_dup(x + j, W));
+      }
+      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(lo, hi), taps.w[j]));
+    }
+    if (!VERTICAL) acc = fmax(acc, 1.0);  // np.maximum(depth, 1.0)
+    out[i] = (OT)acc;
+  }
+}
+
+}  // namespace
+}  // namespace awx
+
+using namespace awx;
+
+extern "C" size_t awx_corrupt_workspace_bytes(int64_t batch, int32_t height, int32_t width) {
+  if (batch <= 0 || height <= 0 || width <= 0) return 0;
+  const size_t ww = (size_t)(width + 31) / 32;
+  return params_bytes(batch) + (size_t)batch * height * ww * sizeof(unsigned);
+}
+
+extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int32_t H, int32_t W,
+                           const AwxCorruptParams* params, const void* field, int32_t field_dtype, const int32_t* items,
+                           int64_t n_items, void* workspace, void* stream) {
+  AWX_REQUIRE(batch >= 0 && H >= 0 && W >= 0, AWX_E_ARG, "awx_corrupt: negative size");
+  if (batch == 0 || H == 0 || W == 0) return AWX_OK;
+  AWX_REQUIRE(img && out && params && workspace, AWX_E_ARG, "awx_corrupt: NULL pointer (img/out/params/workspace)");
+  AWX_REQUIRE(batch <= 65535, AWX_E_UNSUPPORTED, "awx_corrupt: batch %lld > 65535 per call", (long long)batch);
+  AWX_REQUIRE(field_dtype == AWX_F32 || field_dtype == AWX_F64, AWX_E_ARG, "awx_corrupt: unknown field dtype %d", field_dtype);
+  bool any_point = false, any_overlay = false, blur3 = false, blur7 = false;
+  for (int64_t b = 0; b < batch; ++b) {
+    const AwxCorruptParams& q = params[b];
+    switch (q.kind) {
+      case AWX_CLEAN: any_point = true; break;
+      case AWX_FOG:
+      case AWX_NIGHT:
+        any_point = true;
+        AWX_REQUIRE(field != nullptr, AWX_E_ARG, "awx_corrupt: image %lld (fog/night) needs a depth/noise field", (long long)b);
+        AWX_REQUIRE(q.field_offset >= 0, AWX_E_ARG, "awx_corrupt: negative field offset");
+        break;
+      case AWX_RAIN:
+      case AWX_SNOW:
+        any_overlay = true;
+        AWX_REQUIRE(q.blur_k == 3 || q.blur_k == 7, AWX_E_UNSUPPORTED, "awx_corrupt: blur kernel %d (3 or 7 supported)", q.blur_k);
+        AWX_REQUIRE(q.item_count >= 0 && q.item_begin >= 0 && (int64_t)q.item_begin + q.item_count <= n_items, AWX_E_ARG,
+                    "awx_corrupt: image %lld item range [%d,+%d) outside %lld items", (long long)b, q.item_begin, q.item_count, (long long)n_items);
+        AWX_REQUIRE(q.item_count == 0 || items != nullptr, AWX_E_ARG, "awx_corrupt: items is NULL");
+        (q.blur_k == 3 ? blur3 : blur7) = true;
+        break;
+      default:
+        set_error("awx_corrupt: unknown kind %d for image %lld", q.kind, (long long)b);
+        return AWX_E_ARG;
+    }
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  AwxCorruptParams* dparams = static_cast<AwxCorruptParams*>(workspace);
+  AWX_CUDA(cudaMemcpyAsync(dparams, params, (size_t)batch * sizeof(AwxCorruptParams), cudaMemcpyHostToDevice, s));
+  const long long HW = (long long)H * W;
+  if (any_point) {
+    long long chunks = (HW + kChunkPx - 1) / kChunkPx;
+    const long long cap = (long long)sm_count() * 16;
+    dim3 grid((unsigned)(chunks < cap ? chunks : cap), (unsigned)batch);
+    if (field_dtype == AWX_F64)
+      pointwise_kernel<double><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW);
+    else
+      pointwise_kernel<float><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const float*>(field), HW);
+    AWX_CUDA(cudaGetLastError());
+  }
+  if (any_overlay) {
+    const int WW = (W + 31) / 32;
+    unsigned* mask = reinterpret_cast<unsigned*>(static_cast<unsigned char*>(workspace) + params_bytes(batch));
+    AWX_CUDA(cudaMemsetAsync(mask, 0, (size_t)batch * H * WW * sizeof(unsigned), s));
+    rasterize_kernel<<<dim3(4, (unsigned)batch), 128, 0, s>>>(dparams, items, mask, H, W, WW);
+    AWX_CUDA(cudaGetLastError());
+    int rc = AWX_OK;
+    if (blur3) rc = launch_blur<1>(img, out, dparams, mask, batch, H, W, WW, s);
+    if (rc != AWX_OK) return rc;
+    if (blur7) rc = launch_blur<3>(img, out, dparams, mask, batch, H, W, WW, s);
+    if (rc != AWX_OK) return rc;
+  }
+  return AWX_OK;
+}
+
+extern "C" int awx_synth_depth(const double* noise, void* out, int32_t out_dtype, double* tmp, int64_t batch, int32_t H,
+                               int32_t W, double depth_scale, const double* weights, int32_t radius, void* stream) {
+  AWX_REQUIRE(batch >= 0 && H >= 0 && W >= 0, AWX_E_ARG, "awx_synth_depth: negative size");
+  if (batch == 0 || H == 0 || W == 0) return AWX_OK;
+  AWX_REQUIRE(noise && out && tmp && weights, AWX_E_ARG, "awx_synth_depth: NULL pointer");
+  AWX_REQUIRE(radius >= 0 && radius <= 32, AWX_E_UNSUPPORTED, "awx_synth_depth: radius %d outside 0..32", radius);
+  AWX_REQUIRE(out_dtype == AWX_F32 || out_dtype == AWX_F64, AWX_E_ARG, "awx_synth_depth: unknown out dtype");
+  GaussTaps taps{};
+  taps.radius = radius;
+  for (int j = 0; j <= radius; ++j) taps.w[j] = weights[radius + j];
+  const long long total = (long long)batch * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  depth_pass_kernel<true, double><<<(unsigned)blocks, 256, 0, s>>>(noise, tmp, H, W, total, taps, depth_scale);
+  AWX_CUDA(cudaGetLastError());
+  if (out_dtype == AWX_F64)
+    depth_pass_kernel<false, double><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<double*>(out), H, W, total, taps, depth_scale);
+  else
+    depth_pass_kernel<false, float><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<float*>(out), H, W, total, taps, depth_scale);
+  AWX_CUDA(cudaGetLastError());
+  return AWX_OK;
+}

@@ -41,6 +41,10 @@ class IoUMetrics:
             # channel count differs from num_classes: the reference still indexes a
             # num_classes x num_classes matrix with t*num_classes + argmax -> go through the map
             predictions = ops.score(_as_logits(predictions), want_pred=torch.int64)["pred"]
+        # `targets * C + predictions` must promote to int64 or the reference's index_add_ raises
+        if torch.promote_types(targets.dtype, predictions.dtype) != torch.int64:
+            raise RuntimeError("index_add_(): self (Long) and source "
+                               f"({torch.promote_types(targets.dtype, predictions.dtype)}) must have the same scalar type")
         cm_d, cnt_d = ops.confusion(predictions, targets, self.num_classes, self.ignore_index)
         cnt = cnt_d.cpu().numpy()
         return cm_d.cpu().numpy(), int(cnt[_lib.CNT_VALID]), int(cnt[_lib.CNT_CORRECT]), int(cnt[_lib.CNT_BAD_LABEL])

@@ -1,0 +1,201 @@
+"""Drop-in ``EnsembleModel`` (fusion part) and ``FogDensityAwareLoss`` (reference: models/model.py:377-677).
+
+The SegFormer / DeepLabV3+ backbones stay ordinary PyTorch producers of logits (north-star); this
+module owns what happens to their outputs: logit fusion, temperature scaling, the disagreement
+map and the fog-density-aware loss -- all computed by libawx.so.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib, ops, ops_loss
+
+logger = logging.getLogger(__name__)
+
+_STRATEGY = {"weighted_average": _lib.FUSE_WEIGHTED, "max_confidence": _lib.FUSE_MAXCONF}
+
+
+def _reference_backbones(num_classes: int, include_depth: bool):
+    """The stock members, if the reference package is importable; otherwise the caller injects its own."""
+    try:
+        from adverse_weather_semantic_segmentation_robustness_benchmark.models.model import (  # type: ignore
+            SegFormerModel, DeepLabV3PlusModel)
+    except Exception as exc:  # pragma: no cover - depends on the environment
+        raise RuntimeError(
+            "EnsembleModel needs two logits producers: pass segformer=/deeplabv3plus= modules returning "
+            "{'segmentation': [B,C,H,W][, 'depth': [B,1,H,W]]}, or install the reference package for its "
+            f"stock backbones ({exc})") from exc
+    return (SegFormerModel(num_classes=num_classes, include_depth=include_depth),
+            DeepLabV3PlusModel(num_classes=num_classes, include_depth=include_depth))
+
+
+class EnsembleModel(nn.Module):
+    """Two-member ensemble with learnable fusion weights and temperature (models/model.py:377-513).
+
+    Same constructor arguments, parameters (``ensemble_weights[2]``, ``temperature[1]``), output
+    keys and strategies as the reference; ``segformer`` / ``deeplabv3plus`` may be injected."""
+
+    def __init__(self, num_classes: int = 19, include_depth: bool = True,
+                 ensemble_strategy: str = "weighted_average", temperature_scaling: bool = True,
+                 segformer: Optional[nn.Module] = None, deeplabv3plus: Optional[nn.Module] = None) -> None:
+        super().__init__()
+        self.num_classes = num_classes
+        self.include_depth = include_depth
+        self.ensemble_strategy = ensemble_strategy
+        self.temperature_scaling = temperature_scaling
+        if segformer is None or deeplabv3plus is None:
+            segformer, deeplabv3plus = _reference_backbones(num_classes, include_depth)
+        self.segformer = segformer
+        self.deeplabv3plus = deeplabv3plus
+        self.ensemble_weights = nn.Parameter(torch.ones(2) / 2)
+        if self.temperature_scaling:
+            self.temperature = nn.Parameter(torch.ones(1))
+        logger.info(f"Initialized ensemble model with {ensemble_strategy} strategy (libawx fusion)")
+
+    # -- fusion -------------------------------------------------------------------------------
+    def _fusion_scalars(self):
+        """Host copies of softmax(ensemble_weights) (fp32, model.py:444) and the temperature."""
+        w = F.softmax(self.ensemble_weights.detach().float().cpu(), dim=0)
+        temp = float(self.temperature.detach().float().cpu()[0]) if self.temperature_scaling else None
+        return float(w[0]), float(w[1]), temp
+
+    def fuse(self, seg1: torch.Tensor, seg2: torch.Tensor) -> torch.Tensor:
+        """Fused, temperature-scaled logits (model.py:443-462), bit-exact w.r.t. torch eager."""
+        if torch.is_grad_enabled() and (seg1.requires_grad or seg2.requires_grad
+                                        or self.ensemble_weights.requires_grad and self.training):
+            return _FuseFn.apply(seg1, seg2, self.ensemble_weights,
+                                 self.temperature if self.temperature_scaling else None,
+                                 self.ensemble_strategy)
+        w0, w1, temp = self._fusion_scalars()
+        code = _STRATEGY.get(self.ensemble_strategy, _lib.FUSE_MEAN)
+        return ops.score(seg1, seg2, strategy=code, w0=w0, w1=w1, temperature=temp, want_fused=True)["fused"]
+
+    def fuse_depth(self, d1: torch.Tensor, d2: torch.Tensor) -> torch.Tensor:
+        """model.py:471-478: weighted for weighted_average, plain mean otherwise; no temperature."""
+        if torch.is_grad_enabled() and (d1.requires_grad or d2.requires_grad):
+            if self.ensemble_strategy == "weighted_average":
+                w = F.softmax(self.ensemble_weights, dim=0)
+                return w[0] * d1 + w[1] * d2
+            return (d1 + d2) / 2
+        w0, w1, _ = self._fusion_scalars()
+        code = _lib.FUSE_WEIGHTED if self.ensemble_strategy == "weighted_average" else _lib.FUSE_MEAN
+        return ops.score(d1, d2, strategy=code, w0=w0, w1=w1, temperature=None, want_fused=True)["fused"]
+
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        o1 = self.segformer(x)
+        o2 = self.deeplabv3plus(x)
+        results = {
+            "segmentation": self.fuse(o1["segmentation"], o2["segmentation"]),
+            "segformer_seg": o1["segmentation"],
+            "deeplabv3plus_seg": o2["segmentation"],
+        }
+        if self.include_depth:
+            results.update({
+                "depth": self.fuse_depth(o1["depth"], o2["depth"]),
+                "segformer_depth": o1["depth"],
+                "deeplabv3plus_depth": o2["depth"],
+            })
+        return results
+
+    def get_ensemble_disagreement(self, x: torch.Tensor) -> torch.Tensor:
+        """model.py:488-513: 0.5*[KL(m||p)+KL(m||q)] of the two members' softmaxes, [B,H,W], no grad."""
+        with torch.no_grad():
+            o1 = self.segformer(x)
+            o2 = self.deeplabv3plus(x)
+            return ops.score(o1["segmentation"], o2["segmentation"], strategy=_lib.FUSE_MEAN, want_js=True)["js"]
+
+
+class _FuseFn(torch.autograd.Function):
+    """Differentiable fusion for training: forward through awx_score; backward is the closed form
+    of d(w0*a + w1*b)/T (weights go through their softmax), evaluated with torch reductions since
+    it is two scaled copies of the incoming gradient plus three dot products."""
+
+    @staticmethod
+    def forward(ctx, a, b, raw_w, temperature, strategy):
+        w = F.softmax(raw_w.detach().float(), dim=0)
+        w0, w1 = float(w[0]), float(w[1])
+        temp = None if temperature is None else float(temperature.detach().float().reshape(-1)[0])
+        code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
+        out = ops.score(a, b, strategy=code, w0=w0, w1=w1, temperature=temp, want_fused=True,
+                        want_conf=False)
+        fused = out["fused"]
+        ctx.save_for_backward(a, b, raw_w, temperature if temperature is not None else torch.ones(1), fused)
+        ctx.has_temp = temperature is not None
+        ctx.strategy = strategy
+        return fused
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, raw_w, temperature, fused = ctx.saved_tensors
+        dev = g.device
+        t = temperature.to(dev).float().reshape(-1)[0] if ctx.has_temp else torch.ones((), device=dev)
+        gs = g / t
+        ga = gb = gw = gt = None
+        if ctx.strategy == "weighted_average":
+            w = F.softmax(raw_w.to(dev).float(), dim=0)
+            ga, gb = gs * w[0], gs * w[1]
+            dots = torch.stack([(gs * a.to(dev)).sum(), (gs * b.to(dev)).sum()])
+            # softmax Jacobian: dL/draw_i = w_i * (dots_i - sum_j w_j dots_j)
+            gw = (w * (dots - (w * dots).sum())).to(raw_w.dtype).to(raw_w.device)
+        elif ctx.strategy == "max_confidence":
+            ca = F.softmax(a.to(dev), dim=1).max(dim=1)[0]
+            cb = F.softmax(b.to(dev), dim=1).max(dim=1)[0]
+            pick = (ca > cb).float().unsqueeze(1)
+            ga, gb = gs * pick, gs * (1 - pick)
+        else:
+            ga, gb = gs * 0.5, gs * 0.5
+        if ctx.has_temp:
+            gt = (-(g * fused).sum() / t).reshape(temperature.shape).to(temperature.dtype).to(temperature.device)
+        return ga.to(a.device), gb.to(b.device), gw, gt, None
+
+
+class FogDensityAwareLoss(nn.Module):
+    """Fog-density-aware loss (models/model.py:516-677): per-pixel CE/focal times (1 + s*fog_density),
+    plus depth MSE; forward AND gradients come from one awx_fogloss launch."""
+
+    def __init__(self, base_loss: str = "cross_entropy", depth_weight: float = 0.5,
+                 fog_sensitivity: float = 2.0, depth_loss_weight: float = 0.1) -> None:
+        super().__init__()
+        self.base_loss = base_loss
+        self.depth_weight = depth_weight
+        self.fog_sensitivity = fog_sensitivity
+        self.depth_loss_weight = depth_loss_weight
+        logger.info(f"Initialized FogDensityAwareLoss with {base_loss} base loss (libawx)")
+
+    def forward(self, predictions: Dict[str, torch.Tensor], targets: Dict[str, torch.Tensor],
+                fog_density: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        seg_pred = predictions["segmentation"]
+        label = targets["label"]
+        use_depth = "depth" in predictions and self.depth_weight > 0
+        pred_depth = predictions["depth"].squeeze(1) if use_depth else None
+        if use_depth and fog_density is None:
+            # model.py:593-597: density estimated from the predicted depth (global min/max and mean
+            # gradient magnitude); autograd flows into the depth head through it
+            fog_density = self._estimate_fog_density_from_depth(pred_depth)
+        depth_tgt = targets["depth"] if (use_depth and "depth" in targets) else None
+        seg, dep = ops_loss.fog_loss_terms(seg_pred, pred_depth if depth_tgt is not None else None, label,
+                                           fog_density, depth_tgt, self.fog_sensitivity,
+                                           self.base_loss == "focal")
+        depth_loss = dep if depth_tgt is not None else 0.0
+        total = seg + self.depth_loss_weight * depth_loss
+        return {"total_loss": total, "segmentation_loss": seg, "depth_loss": depth_loss}
+
+    def _estimate_fog_density_from_depth(self, depth: torch.Tensor) -> torch.Tensor:
+        """model.py:644-677.  Host-side glue in torch ops (a [B,H,W] map, 4 B/px, three global
+        scalars); kept differentiable so that path B trains the depth head as the reference does."""
+        depth = ops.to_device(depth, torch.float32) if not depth.is_cuda else depth
+        unit = (depth - depth.min()) / (depth.max() - depth.min() + 1e-8)
+        density = unit * 0.7
+        gx = torch.abs(depth[:, :, 1:] - depth[:, :, :-1])
+        gy = torch.abs(depth[:, 1:, :] - depth[:, :-1, :])
+        gx = F.pad(gx, (0, 1, 0, 0), mode="replicate")
+        gy = F.pad(gy, (0, 0, 0, 1), mode="replicate")
+        mag = torch.sqrt(gx ** 2 + gy ** 2 + 1e-8)
+        density = density - (mag > mag.mean()) * 0.3
+        return torch.clamp(density, 0, 1)

@@ -224,3 +224,46 @@ def confusion(pred: torch.Tensor, labels: torch.Tensor, num_classes: int, ignore
                            _ptr(cm), _ptr(cnt), _stream())
     _lib.check(rc, "awx_confusion")
     return cm.view(num_classes, num_classes), cnt
+
+
+def corrupt_workspace(batch: int, height: int, width: int) -> torch.Tensor:
+    n = _lib.load().awx_corrupt_workspace_bytes(batch, height, width)
+    return torch.empty(max(int(n), 16), dtype=torch.uint8, device=require_cuda())
+
+
+def corrupt(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tensor] = None,
+            items: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """awx_corrupt on a device-resident uint8 [B,H,W,3] batch.  `params`: host records
+    (``_lib.CORRUPT_PARAMS_DTYPE``); `field`: device fp32/fp64 depth / noise values; `items`:
+    device int32 [n,5] drops / flakes."""
+    lib = _lib.load()
+    if not images.is_cuda or images.dtype != torch.uint8 or not images.is_contiguous():
+        raise ValueError("images must be a contiguous CUDA uint8 tensor")
+    b, h, w, ch = images.shape
+    if ch != 3:
+        raise ValueError("images must be [B,H,W,3]")
+    if params.dtype != _lib.CORRUPT_PARAMS_DTYPE or len(params) != b:
+        raise ValueError("params must be one CORRUPT_PARAMS_DTYPE record per frame")
+    params = np.ascontiguousarray(params)
+    if out is None:
+        out = torch.empty_like(images)
+    if workspace is None:
+        workspace = corrupt_workspace(b, h, w)
+    fdt = _lib.F64
+    if field is not None:
+        if field.dtype == torch.float32:
+            fdt = _lib.F32
+        elif field.dtype != torch.float64:
+            raise TypeError("field must be float32 or float64")
+        field = field.contiguous()
+    n_items = 0
+    if items is not None:
+        if items.dtype != torch.int32:
+            raise TypeError("items must be int32 [n,5]")
+        items = items.contiguous()
+        n_items = items.shape[0]
+    rc = lib.awx_corrupt(_ptr(images), _ptr(out), b, h, w, params.ctypes.data_as(C.c_void_p), _ptr(field), fdt,
+                         _ptr(items), n_items, _ptr(workspace), _stream())
+    _lib.check(rc, "awx_corrupt")
+    return out

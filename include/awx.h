@@ -151,13 +151,13 @@ int awx_member_variance(const float* logits_a, const float* logits_b, float* out
 enum { AWX_CLEAN = 0, AWX_FOG = 1, AWX_RAIN = 2, AWX_SNOW = 3, AWX_NIGHT = 4 };
 enum { AWX_F32 = 0, AWX_F64 = 1 };
 
-/* One per image (device array).  Field/overlay offsets are in ELEMENTS of the arrays
- * passed to awx_corrupt. */
+/* One per image (HOST array; awx_corrupt copies it into the head of its workspace).
+ * Field/overlay offsets are in ELEMENTS of the arrays passed to awx_corrupt. */
 typedef struct AwxCorruptParams {
   int32_t kind;        /* AWX_CLEAN..AWX_NIGHT                                              */
   int32_t blur_k;      /* rain: 3; snow: 3 or 7                                             */
   double d0;           /* fog: beta            night: intensity (noise*intensity*0.5, fp64) */
-  double d1;           /* fog: airlight A                                                   */
+  double d1;           /* fog: airlight A rounded to fp32 (the reference's A*ones_like(fp32)) */
   float f0;            /* rain: fp32(1-haze)   snow: fp32(0.2*I)   night: fp32(1 - I*u)     */
   float f1;            /* rain: fp32(haze*0.7)                                              */
   float taps[4];       /* rain/snow: half Gaussian kernel, taps[0] = centre                 */
@@ -166,35 +166,45 @@ typedef struct AwxCorruptParams {
   int32_t item_count;
 } AwxCorruptParams;
 
-/* items: int32 [n,5].  rain: x0,y0,x1,y1,thickness (cv2.line, preprocessing.py:160);
- * snow: x,y,radius,0,0 (cv2.circle filled, :194).
- * field: depth (fog, :227-248 output) or Gaussian noise (night, :222), fp32 or fp64.
- * mask_ws: workspace of awx_corrupt_workspace_bytes() bytes, needed only when a rain or snow
- * image is present; the call clears and fills it itself.
- * img / out: uint8 [B,H,W,3]; `out` of an AWX_CLEAN image is a copy of `img`. */
+/* items: int32 [n,5] (device).  rain: x0,y0,x1,y1,thickness (cv2.line, preprocessing.py:160);
+ * snow: x,y,radius,0,0 (cv2.circle filled, :194).  Scan conversion happens on the device and
+ * reproduces OpenCV's footprints bit for bit (csrc/raster.cuh, tests/test_raster_cpu.py).
+ * field (device): depth (fog, :227-248 output) or Gaussian noise (night, :222), fp32 or fp64.
+ * workspace (device): awx_corrupt_workspace_bytes() bytes = params copy + 1 bit/pixel overlay
+ * mask; always required; the call fills it itself.
+ * img / out: uint8 [B,H,W,3] (device); `out` of an AWX_CLEAN image is a copy of `img`. */
 size_t awx_corrupt_workspace_bytes(int64_t batch, int32_t height, int32_t width);
 
 int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int32_t height, int32_t width,
-                const AwxCorruptParams* params, const void* field, int32_t field_dtype,
-                const int32_t* items, int64_t n_items, void* mask_ws, void* stream);
+                const AwxCorruptParams* params /*HOST*/, const void* field, int32_t field_dtype,
+                const int32_t* items, int64_t n_items, void* workspace, void* stream);
 
-/* depth = max(gaussian_filter(ramp + noise, sigma=2, reflect), 1) in fp64
- * (_generate_synthetic_depth, preprocessing.py:235-246).  noise: fp64 [B,H,W] drawn by the
- * host; out: fp64 or fp32 [B,H,W]; tmp: fp64 [B,H,W] workspace. */
+/* depth = max(gaussian_filter(ramp + noise, sigma, mode=reflect), 1) in fp64, axis 0 then axis 1,
+ * with scipy's symmetric accumulation order (_generate_synthetic_depth, preprocessing.py:235-246).
+ * noise: fp64 [B,H,W] drawn by the host; out: fp64 or fp32 [B,H,W]; tmp: fp64 [B,H,W] workspace;
+ * weights: HOST fp64 [2*radius+1] normalised Gaussian taps (sigma=2, truncate=4 -> radius 8). */
 int awx_synth_depth(const double* noise, void* out, int32_t out_dtype, double* tmp,
-                    int64_t batch, int32_t height, int32_t width, double depth_scale, void* stream);
+                    int64_t batch, int32_t height, int32_t width, double depth_scale,
+                    const double* weights /*HOST*/, int32_t radius, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fog-density-aware loss, forward + unscaled gradients in one pass
  * (FogDensityAwareLoss.forward, models/model.py:560-617; focal :619-642).
  * sums[0] = sum_i w_i * loss_i, sums[1] = sum_i (depth_pred-depth_tgt)^2 (fp64, device).
  * dlogits (nullable) = w_i * dloss_i/dlogit / N ; ddepth (nullable) = 2*(pred-tgt)/N.
+ * dfog (nullable) = s * base_loss_i / N, the gradient w.r.t. fog_density (model.py:593-597 path).
+ * sums accumulates (zero it first); per-CTA partials go through `workspace`
+ * (awx_fogloss_workspace_bytes() bytes) and are reduced in a fixed order: bit-reproducible.
+ * bad_labels (device int64, nullable): count of labels outside [0,C) -- torch raises on those.
  * ---------------------------------------------------------------------------------- */
+size_t awx_fogloss_workspace_bytes(void);
+
 int awx_fogloss(const float* logits, const void* labels, int32_t label_dtype,
                 const float* fog_density /*nullable*/, const float* depth_pred /*nullable*/,
                 const float* depth_tgt /*nullable*/, float fog_sensitivity, int32_t focal,
                 int64_t batch, int32_t num_classes, int64_t pixels_per_image,
-                double* sums, float* dlogits, float* ddepth, int64_t* bad_labels, void* stream);
+                double* sums, float* dlogits, float* ddepth, float* dfog /*nullable*/,
+                int64_t* bad_labels, void* workspace, void* stream);
 
 /* x[i] *= *scale (device scalar) -- backward of a mean-reduced loss with grad_output != 1. */
 int awx_scale_inplace(float* x, int64_t n, const float* scale, void* stream);

@@ -1,0 +1,146 @@
+"""GPU parity: awx_corrupt / awx_synth_depth / WeatherDegradationTransforms against the oracle and the
+golden vectors produced by the reference.
+
+Bars: corrupted images within 1 LSB of the reference (the count of +-1 pixels
+is asserted small and printed); fog and night with fp64 fields are expected to be EXACT (same fp64
+expression order, truncation); the synthetic depth is bit-exact with scipy's filter.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import weather as ow
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def wdt():
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.data.preprocessing import (
+        WeatherDegradationTransforms)
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import _lib
+    _lib.load()
+    return WeatherDegradationTransforms
+
+
+def _diff(got, want):
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    return int(d.max()), float((d > 0).mean())
+
+
+@pytest.mark.parametrize("tag", ["s", "m"])
+@pytest.mark.parametrize("kind", ["fog", "rain", "snow", "night"])
+@pytest.mark.parametrize("seed,intensity", [(42, None), (43, 0.5), (44, 0.9)])
+def test_golden_apply_weather_effect(wdt, golden, tag, kind, seed, intensity):
+    """Same seed -> same host draws -> image within 1 LSB of the reference's output."""
+    g = golden("weather")
+    img = g[f"{tag}_image"]
+    t = wdt(seed=seed)
+    got = t.apply_weather_effect(img.copy(), kind, intensity)
+    want = g[f"{tag}_{kind}_seed{seed}"]
+    assert got.dtype == np.uint8 and got.shape == want.shape
+    mx, frac = _diff(got, want)
+    assert mx <= 1, f"{kind}: max diff {mx}"
+    if kind in ("fog", "night"):
+        assert mx == 0, f"{kind} with fp64 field must be exact, {frac:.2e} of values differ"
+    else:
+        assert frac < 2e-3, f"{kind}: {frac:.2e} of values differ by 1 LSB"
+
+
+@pytest.mark.parametrize("kind,intensity", [("rain", 0.8), ("snow", 0.7)])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_golden_border_overlays(wdt, golden, kind, intensity, seed):
+    g = golden("weather")
+    got = wdt(seed=seed).apply_weather_effect(g["b_image"].copy(), kind, intensity)
+    mx, frac = _diff(got, g[f"b_{kind}_seed{seed}"])
+    assert mx <= 1 and frac < 5e-3
+
+
+@pytest.mark.parametrize("tag,shape", [("s", (40, 56)), ("m", (96, 160))])
+def test_synthetic_depth_bit_exact(wdt, golden, tag, shape):
+    g = golden("weather")
+    t = wdt(seed=11)
+    d = t._generate_synthetic_depth(*shape)
+    assert d.dtype == np.float64
+    assert np.array_equal(d, g[f"{tag}_depth_seed11"]), f"max diff {np.abs(d - g[f'{tag}_depth_seed11']).max():.3e}"
+
+
+def test_clean_alias_and_errors(wdt):
+    t = wdt(seed=0)
+    img = np.zeros((8, 8, 3), np.uint8)
+    assert t.apply_weather_effect(img, "clean") is img
+    with pytest.raises(ValueError, match="Unknown weather type"):
+        t.apply_weather_effect(img, "hail")
+
+
+@pytest.mark.parametrize("h,w", [(64, 128), (50, 70), (17, 33), (128, 256)])
+def test_batch_mixed_kinds_vs_oracle(wdt, h, w):
+    """One awx_corrupt call over a batch with every kind (incl. clean copy), ragged sizes included."""
+    t = wdt(seed=123)
+    rng = np.random.RandomState(h * w)
+    kinds = ["clean", "fog", "rain", "snow", "night", "snow", "rain", "fog"]
+    imgs = rng.randint(0, 255, (len(kinds), h, w, 3)).astype(np.uint8)
+    draws = [t.draw(k, h, w) for k in kinds]
+    # make sure both blur sizes occur
+    draws[3].blur_k, draws[5].blur_k = 3, 7
+    for d in draws:
+        if d.kind == "fog":
+            d.depth = ow.depth_from_noise(d.depth_noise)
+    out = t.corrupt_batch(imgs, draws).cpu().numpy()
+    n_off = 0
+    for i, d in enumerate(draws):
+        if d.kind == "clean":
+            want = imgs[i]
+        elif d.kind == "fog":
+            want = ow.fog_apply(imgs[i], d.depth, d.intensity)
+        elif d.kind == "rain":
+            want = ow.rain_apply(imgs[i], d.intensity, d.items)
+        elif d.kind == "snow":
+            want = ow.snow_apply(imgs[i], d.intensity, d.items[:, :3], d.blur_k)
+        else:
+            want = ow.night_apply(imgs[i], d.intensity, d.reduction, d.noise)
+        mx, frac = _diff(out[i], want)
+        assert mx <= 1, (d.kind, mx)
+        if d.kind in ("clean", "fog", "night"):
+            assert mx == 0, (d.kind, frac)
+        n_off += frac
+    assert n_off / len(kinds) < 1e-3
+
+
+def test_fp32_fields_within_one_lsb(wdt):
+    """fp32 depth / noise (10 and 18 B/px instead of 14 and 30): still within 1 LSB."""
+    t = wdt(seed=5)
+    h, w = 96, 160
+    rng = np.random.RandomState(1)
+    imgs = rng.randint(0, 255, (2, h, w, 3)).astype(np.uint8)
+    draws = [t.draw("fog", h, w, 0.6), t.draw("night", h, w, 0.7)]
+    draws[0].depth = ow.depth_from_noise(draws[0].depth_noise)
+    out = t.corrupt_batch(imgs, draws, field_dtype=np.float32).cpu().numpy()
+    mx, frac = _diff(out[0], ow.fog_apply(imgs[0], draws[0].depth, draws[0].intensity))
+    assert mx <= 1 and frac < 1e-3
+    mx, frac = _diff(out[1], ow.night_apply(imgs[1], draws[1].intensity, draws[1].reduction, draws[1].noise))
+    assert mx <= 1 and frac < 1e-3
+
+
+def test_full_size_properties(wdt):
+    """1024x2048 frames: clean is the identity; heavy snow only brightens; output deterministic."""
+    t = wdt(seed=9)
+    h, w = 1024, 2048
+    rng = np.random.RandomState(2)
+    imgs = rng.randint(0, 255, (3, h, w, 3)).astype(np.uint8)
+    draws = [t.draw("clean", h, w), t.draw("snow", h, w, 0.7), t.draw("rain", h, w, 0.8)]
+    a = t.corrupt_batch(imgs, draws)
+    b = t.corrupt_batch(imgs, draws)
+    assert torch.equal(a, b)
+    a = a.cpu().numpy()
+    assert np.array_equal(a[0], imgs[0])
+    # snow: clip(x + 0.14) blurred with white discs on top can never be darker than a 7x7 min filter of x
+    assert a[1].mean() > imgs[1].mean()
+    # spot-check a tile against the oracle (border tile and interior tile)
+    want = ow.snow_apply(imgs[1], draws[1].intensity, draws[1].items[:, :3], draws[1].blur_k)
+    mx, frac = _diff(a[1], want)
+    assert mx <= 1 and frac < 1e-3
+    want = ow.rain_apply(imgs[2], draws[2].intensity, draws[2].items)
+    mx, frac = _diff(a[2], want)
+    assert mx <= 1 and frac < 1e-3

@@ -1,0 +1,175 @@
+"""GPU parity: awx_fogloss / FogDensityAwareLoss / EnsembleModel against golden vectors of the reference.
+
+Bars: loss values rel 1e-5; gradients |d| <= 1e-5*|ref| + 1e-9 (they carry a 1/N factor);
+fused logits bit-exact; disagreement map |d| <= 1e-5*|ref| + 2e-6.
+"""
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import adverse_weather_semantic_segmentation_robustness_benchmark_b200 as p
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import _lib
+    _lib.load()
+    return p
+
+
+VARIANTS = {
+    "ce_fd_depth": ("cross_entropy", True, True, True),
+    "ce_fd_nodepth": ("cross_entropy", True, False, False),
+    "ce_nofd_nodepth": ("cross_entropy", False, False, False),
+    "focal_fd_depth": ("focal", True, True, True),
+    "ce_pathB": ("cross_entropy", False, True, True),
+    "ce_fd_dpred_only": ("cross_entropy", True, True, False),
+}
+
+
+def _close(got, want, rtol, atol):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    ex = np.abs(got - want) - (atol + rtol * np.abs(want))
+    assert ex.max() <= 0, f"max abs diff {np.abs(got - want).max():.3e}, excess {ex.max():.3e}"
+
+
+@pytest.mark.parametrize("tag", sorted(VARIANTS))
+@pytest.mark.parametrize("device", ["cuda", "cpu"])
+def test_loss_forward_backward_golden(pkg, golden, tag, device):
+    g = golden("loss")
+    base, use_fd, dpred, dtgt = VARIANTS[tag]
+    lg = torch.from_numpy(g["logits"]).to(device).requires_grad_(True)
+    dp = torch.from_numpy(g["depth"]).to(device).requires_grad_(True)
+    pred = {"segmentation": lg}
+    tgt = {"label": torch.from_numpy(g["label"]).to(device)}
+    if dpred:
+        pred["depth"] = dp
+    if dtgt:
+        tgt["depth"] = torch.from_numpy(g["dtgt"]).to(device)
+    fn = pkg.FogDensityAwareLoss(base_loss=base)
+    r = fn(pred, tgt, torch.from_numpy(g["fd"]).to(device) if use_fd else None)
+    assert set(r) == {"total_loss", "segmentation_loss", "depth_loss"}
+    r["total_loss"].backward()
+    _close(r["total_loss"].item(), g[f"{tag}_total"], 1e-5, 0)
+    _close(r["segmentation_loss"].item(), g[f"{tag}_seg"], 1e-5, 0)
+    dl = r["depth_loss"]
+    _close(dl.item() if torch.is_tensor(dl) else dl, g[f"{tag}_depthloss"], 1e-5, 0)
+    assert lg.grad.device.type == device
+    _close(lg.grad.cpu().numpy(), g[f"{tag}_dlogits"], 1e-5, 1e-9)
+    want = g[f"{tag}_ddepth"]
+    if want.size:
+        _close(dp.grad.cpu().numpy(), want, 2e-5, 1e-9)
+    else:
+        assert dp.grad is None
+
+
+def test_loss_bad_label_raises(pkg):
+    fn = pkg.FogDensityAwareLoss()
+    lg = torch.zeros(1, 19, 4, 4)
+    with pytest.raises(IndexError):
+        fn({"segmentation": lg}, {"label": torch.full((1, 4, 4), 255)})
+
+
+def test_loss_uint8_labels_and_odd_sizes(pkg):
+    from oracle import loss as ol
+    torch.manual_seed(0)
+    for c, h, w in ((19, 33, 35), (5, 16, 24), (19, 64, 64)):
+        lg = torch.randn(2, c, h, w, requires_grad=True)
+        lab = torch.randint(0, c, (2, h, w)).to(torch.uint8)
+        fd = torch.rand(2, h, w)
+        want = ol.fog_loss({"segmentation": lg}, {"label": lab}, fd)
+        want["total_loss"].backward()
+        gref = lg.grad.clone()
+        lg.grad = None
+        got = pkg.FogDensityAwareLoss()({"segmentation": lg}, {"label": lab}, fd)
+        got["total_loss"].backward()
+        _close(got["total_loss"].item(), want["total_loss"].item(), 1e-5, 0)
+        _close(lg.grad.numpy(), gref.numpy(), 1e-5, 1e-9)
+        lg.grad = None
+
+
+def test_loss_deterministic(pkg):
+    torch.manual_seed(1)
+    lg = torch.randn(4, 19, 128, 128, device="cuda")
+    lab = torch.randint(0, 19, (4, 128, 128), device="cuda")
+    fd = torch.rand(4, 128, 128, device="cuda")
+    fn = pkg.FogDensityAwareLoss()
+    a = fn({"segmentation": lg}, {"label": lab}, fd)["total_loss"]
+    b = fn({"segmentation": lg}, {"label": lab}, fd)["total_loss"]
+    assert a.item() == b.item()
+
+
+class _Fixed(nn.Module):
+    def __init__(self, seg, depth=None):
+        super().__init__()
+        self.seg, self.depth = seg, depth
+
+    def forward(self, x):
+        out = {"segmentation": self.seg}
+        if self.depth is not None:
+            out["depth"] = self.depth
+        return out
+
+
+@pytest.mark.parametrize("strategy", ["weighted_average", "max_confidence", "mean_anything"])
+@pytest.mark.parametrize("ts", [True, False])
+def test_ensemble_model_golden(pkg, golden, strategy, ts):
+    g = golden("fusion")
+    l1, l2 = torch.from_numpy(g["l1"]), torch.from_numpy(g["l2"])
+    d1, d2 = torch.from_numpy(g["d1"]), torch.from_numpy(g["d2"])
+    ens = pkg.EnsembleModel(19, True, strategy, ts, segformer=_Fixed(l1, d1), deeplabv3plus=_Fixed(l2, d2))
+    with torch.no_grad():
+        ens.ensemble_weights.copy_(torch.from_numpy(g["raw_w"]))
+        if ts:
+            ens.temperature.copy_(torch.from_numpy(g["temp"]))
+        r = ens(torch.zeros(2, 3, 24, 40))
+    tag = f"{strategy}_{'T' if ts else 'noT'}"
+    keys = {"segmentation", "segformer_seg", "deeplabv3plus_seg", "depth", "segformer_depth", "deeplabv3plus_depth"}
+    assert set(r) == keys
+    assert torch.equal(r["segmentation"].cpu(), torch.from_numpy(g[f"{tag}_seg"])), "fused logits must be bit-exact"
+    assert torch.equal(r["depth"].cpu(), torch.from_numpy(g[f"{tag}_depth"]))
+    dis = ens.get_ensemble_disagreement(torch.zeros(2, 3, 24, 40))
+    assert dis.shape == (2, 24, 40) and float(dis.min()) >= -1e-6
+    _close(dis.cpu().numpy(), g[f"{tag}_dis"], 1e-5, 2e-6)
+    assert isinstance(ens.temperature if ts else ens.ensemble_weights, nn.Parameter)
+
+
+def test_ensemble_training_gradients(pkg):
+    """Differentiable fusion + loss: gradients w.r.t. members, fusion weights and temperature
+    against torch autograd of the reference's expressions."""
+    from oracle import fusion as of_, loss as ol
+    torch.manual_seed(3)
+    b, c, h, w = 2, 19, 16, 24
+    a0 = torch.randn(b, c, h, w)
+    b0 = torch.randn(b, c, h, w)
+    lab = torch.randint(0, c, (b, h, w))
+    fd = torch.rand(b, h, w)
+
+    def run(ours):
+        a = a0.clone().requires_grad_(True)
+        bb = b0.clone().requires_grad_(True)
+        if ours:
+            ens = pkg.EnsembleModel(c, False, "weighted_average", True, segformer=_Fixed(a), deeplabv3plus=_Fixed(bb))
+            with torch.no_grad():
+                ens.ensemble_weights.copy_(torch.tensor([0.3, 0.9]))
+                ens.temperature.copy_(torch.tensor([1.7]))
+            ens.train()
+            out = ens(torch.zeros(b, 3, h, w))
+            loss = pkg.FogDensityAwareLoss()(out, {"label": lab}, fd)["total_loss"]
+            loss.backward()
+            return loss.item(), a.grad, bb.grad, ens.ensemble_weights.grad, ens.temperature.grad
+        rw = torch.tensor([0.3, 0.9], requires_grad=True)
+        t = torch.tensor([1.7], requires_grad=True)
+        fused = of_.fuse_logits(a, bb, "weighted_average", rw, t)
+        loss = ol.fog_loss({"segmentation": fused}, {"label": lab}, fd)["total_loss"]
+        loss.backward()
+        return loss.item(), a.grad, bb.grad, rw.grad, t.grad
+
+    got, want = run(True), run(False)
+    _close(got[0], want[0], 1e-5, 0)
+    for gg, ww in zip(got[1:], want[1:]):
+        _close(gg.cpu().numpy(), ww.numpy(), 2e-4, 1e-8)
