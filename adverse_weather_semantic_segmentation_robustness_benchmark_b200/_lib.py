@@ -67,6 +67,7 @@ CORRUPT_PARAMS_DTYPE = np.dtype([
 _SIGNATURES = {
     "awx_version": (C.c_int, []),
     "awx_last_error": (C.c_char_p, []),
+    "awx_launch_count": (C.c_int64, []),
     "awx_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "awx_bins_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(BinsLayout)]),
     "awx_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,

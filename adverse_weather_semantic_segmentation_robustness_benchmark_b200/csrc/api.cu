@@ -1,4 +1,6 @@
 // libawx: version, error reporting, device queries.
+#include <atomic>
+
 #include "awx_internal.cuh"
 
 namespace awx {
@@ -17,6 +19,10 @@ int cuda_fail(cudaError_t e, const char* where) {
   return (int)e;
 }
 
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -31,6 +37,8 @@ int sm_count() {
 }
 
 }  // namespace awx
+
+extern "C" int64_t awx_launch_count(void) { return awx::launches(); }
 
 extern "C" int awx_version(void) { return AWX_VERSION; }
 

@@ -31,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* where);
   } while (0)
 
 int sm_count();
+void note_launch(int n = 1);  // counts kernels launched by this library (awx_launch_count)
 
 // --------------------------------------------------------------------- device helpers
 __device__ __forceinline__ float ex2_approx(float x) {

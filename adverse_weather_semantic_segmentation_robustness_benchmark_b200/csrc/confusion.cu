@@ -83,6 +83,7 @@ int launch(const void* pred, const void* lab, long long n, int C, int ign, int64
       static_cast<const P*>(pred), static_cast<const L*>(lab), n, C, ign,
       reinterpret_cast<unsigned long long*>(conf), reinterpret_cast<unsigned long long*>(cnt));
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   return AWX_OK;
 }
 

@@ -270,6 +270,7 @@ int launch_blur(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparam
   dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, (unsigned)B);
   kern<<<grid, kBlurThreads, blur_smem<R>(), s>>>(img, out, dparams, mask, H, W, WW);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   return AWX_OK;
 }
 
@@ -375,6 +376,7 @@ extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int3
     else
       pointwise_kernel<float><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const float*>(field), HW);
     AWX_CUDA(cudaGetLastError());
+  note_launch();
   }
   if (any_overlay) {
     const int WW = (W + 31) / 32;
@@ -382,6 +384,7 @@ extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int3
     AWX_CUDA(cudaMemsetAsync(mask, 0, (size_t)batch * H * WW * sizeof(unsigned), s));
     rasterize_kernel<<<dim3(4, (unsigned)batch), 128, 0, s>>>(dparams, items, mask, H, W, WW);
     AWX_CUDA(cudaGetLastError());
+  note_launch();
     int rc = AWX_OK;
     if (blur3) rc = launch_blur<1>(img, out, dparams, mask, batch, H, W, WW, s);
     if (rc != AWX_OK) return rc;
@@ -408,10 +411,12 @@ extern "C" int awx_synth_depth(const double* noise, void* out, int32_t out_dtype
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   depth_pass_kernel<true, double><<<(unsigned)blocks, 256, 0, s>>>(noise, tmp, H, W, total, taps, depth_scale);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   if (out_dtype == AWX_F64)
     depth_pass_kernel<false, double><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<double*>(out), H, W, total, taps, depth_scale);
   else
     depth_pass_kernel<false, float><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<float*>(out), H, W, total, taps, depth_scale);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   return AWX_OK;
 }

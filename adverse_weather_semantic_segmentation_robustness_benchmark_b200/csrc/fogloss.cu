@@ -175,8 +175,10 @@ int launch_loss(LossParams& p, double* sums, cudaStream_t s) {
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, kThreads, 0, s>>>(p);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   fogloss_finish_kernel<<<1, 32, 0, s>>>(p.partials, (int)blocks, sums);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   return AWX_OK;
 }
 
@@ -247,5 +249,6 @@ extern "C" int awx_scale_inplace(float* x, int64_t n, const float* scale, void* 
   if (blocks > cap) blocks = cap;
   scale_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, scale);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   return AWX_OK;
 }

@@ -472,6 +472,7 @@ int launch_score(const ScoreParams& p, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned)blocks, kThreads, smem, stream>>>(p);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   return AWX_OK;
 }
 
@@ -606,5 +607,6 @@ extern "C" int awx_member_variance(const float* a, const float* b, float* out, i
   if (blocks > cap) blocks = cap;
   variance_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, batch, C, pixels_per_image);
   AWX_CUDA(cudaGetLastError());
+  note_launch();
   return AWX_OK;
 }

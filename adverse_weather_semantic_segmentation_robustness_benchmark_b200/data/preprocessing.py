@@ -120,8 +120,11 @@ class WeatherDegradationTransforms:
         raise ValueError(f"Unknown weather type: {weather_type}")
 
     # ------------------------------------------------------------------ parameter packing
-    def pack(self, draws: Sequence[WeatherDraw], height: int, width: int, field_dtype=np.float64):
-        """AwxCorruptParams records + concatenated field / item arrays for a batch of draws."""
+    def pack(self, draws: Sequence[WeatherDraw], height: int, width: int, field_dtype=np.float64,
+             gather_fields: bool = True):
+        """AwxCorruptParams records + concatenated field / item arrays for a batch of draws.
+        ``gather_fields=False``: the depth / noise fields already live on the device, laid out frame
+        after frame; only their offsets (H*W per fog frame, H*W*3 per night frame) are recorded."""
         prm = np.zeros(len(draws), dtype=_lib.CORRUPT_PARAMS_DTYPE)
         fields: List[np.ndarray] = []
         items: List[np.ndarray] = []
@@ -135,19 +138,19 @@ class WeatherDegradationTransforms:
                 prm[i]["d0"] = b0 + d.intensity * (b1 - b0)
                 # A * np.ones_like(fp32 image) rounds A to fp32 before the fp64 blend (:118)
                 prm[i]["d1"] = np.float64(np.float32(a0 + d.intensity * (a1 - a0)))
-                if d.depth is None:
-                    raise ValueError("fog draw has no depth map; call synthetic_depth() first")
-                fld = np.ascontiguousarray(d.depth, dtype=field_dtype).reshape(-1)
                 prm[i]["field_offset"] = f_off
-                fields.append(fld)
-                f_off += fld.size
+                if gather_fields:
+                    if d.depth is None:
+                        raise ValueError("fog draw has no depth map; call synthetic_depth() first")
+                    fields.append(np.ascontiguousarray(d.depth, dtype=field_dtype).reshape(-1))
+                f_off += height * width
             elif d.kind == "night":
                 prm[i]["d0"] = d.intensity
                 prm[i]["f0"] = np.float32(1 - d.intensity * d.reduction)
-                fld = np.ascontiguousarray(d.noise, dtype=field_dtype).reshape(-1)
                 prm[i]["field_offset"] = f_off
-                fields.append(fld)
-                f_off += fld.size
+                if gather_fields:
+                    fields.append(np.ascontiguousarray(d.noise, dtype=field_dtype).reshape(-1))
+                f_off += height * width * 3
             elif d.kind in ("rain", "snow"):
                 if d.kind == "rain":
                     haze = d.intensity * 0.3

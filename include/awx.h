@@ -41,6 +41,8 @@ extern "C" {
 
 int awx_version(void);
 const char* awx_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+int64_t awx_launch_count(void);
 /* SM count / compute capability of the current device (for grid sizing by callers). */
 int awx_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
