@@ -397,6 +397,8 @@ extern "C" int awx_score(const float* logits_a, const float* logits_b, const voi
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // kernel v2 (TMA ring + packed math) whenever its layout requirements hold; AWX_SCORE_KERNEL=v1
   // forces the generic register-resident kernel (A/B measurements, parity tests of both paths)
+  const char* dbg = getenv("AWX_DEBUG_SKIP_MATH");
+  p.debug_skip = (dbg && dbg[0] == '1') ? 1 : 0;
   const char* force = getenv("AWX_SCORE_KERNEL");
   const bool allow_v2 = !(force && force[0] == 'v' && force[1] == '1');
   if (allow_v2 && score_v2_supported(p)) return launch_score_v2(p, ens, js, s);

@@ -34,6 +34,7 @@ struct ScoreParams {
   float* mi;
   float* js;
   float edges[AWX_MAX_ECE_BINS + 1];
+  int debug_skip;  // AWX_DEBUG_SKIP_MATH=1: consumers only drain the ring (data-movement ceiling; dev only)
 };
 
 struct PixOut {
