@@ -27,7 +27,8 @@ class StreamingEvaluator:
     def __init__(self, num_classes: int = 19, conditions: Sequence[str] = DEFAULT_CONDITIONS,
                  ece_bins: int = 15, auroc_bins: int = ops.DEFAULT_AUROC_BINS,
                  strategy: str = "weighted_average", ensemble_weights: Sequence[float] = (0.5, 0.5),
-                 temperature: Optional[float] = 1.0, ensemble: bool = True, ignore_index: int = 255) -> None:
+                 temperature: Optional[float] = 1.0, ensemble: bool = True, ignore_index: int = 255,
+                 bins_device: Optional[torch.device] = None) -> None:
         self.num_classes = num_classes
         self.conditions = tuple(conditions)
         self.ece_bins = ece_bins
@@ -42,7 +43,10 @@ class StreamingEvaluator:
         self.layout = _lib.bins_layout(num_classes, ece_bins, self.auroc_bins)
         self.words = int(self.layout.total_words)
         # one packed buffer [n_conditions, words]: a single collective merges everything
-        self.bins = torch.zeros((len(self.conditions), self.words), dtype=torch.int64, device=ops.require_cuda())
+        # (bins_device="cpu" exists for the host-side merge/finalise logic and its gloo tests; update()
+        # always needs the CUDA device)
+        dev = ops.require_cuda() if bins_device is None else torch.device(bins_device)
+        self.bins = torch.zeros((len(self.conditions), self.words), dtype=torch.int64, device=dev)
 
     def reset(self) -> None:
         self.bins.zero_()
