@@ -359,7 +359,7 @@ def run_gpu_arm(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(args),
-            "roofline": {"bound": "hbm", "kernel": "score_kernel<19,2,ens> (awx_score)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "score_v2_kernel<weighted,u8 labels,bins only> (awx_score)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": SCORE_BYTES_PER_PX * px_launch,
                          "ms_per_launch": score_ms,
