@@ -375,6 +375,7 @@ extern "C" int awx_score(const float* logits_a, const float* logits_b, const voi
     p.div_mode = 1;
   else
     p.div_mode = 2;
+  p.rT = (float)(1.0 / (double)cfg->temperature);
   p.kz = p.div_mode == 1 ? (float)(1.4426950408889634 / (double)cfg->temperature) : kLog2e;
   p.label_mode = cfg->label_dtype;
   p.ignore_index = cfg->ignore_index;

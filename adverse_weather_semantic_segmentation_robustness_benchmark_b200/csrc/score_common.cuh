@@ -20,6 +20,7 @@ struct ScoreParams {
   float w0, w1, T;
   int div_mode;  // 0: none, 1: T>0 (division only where it can change the argmax), 2: exact everywhere
   float kz;      // log2(e)/T for div_mode 1, log2(e) otherwise
+  float rT;      // fl(1/T), correctly rounded by the host (branch-free exact division, score_v2.cu)
   int label_mode;
   int ignore_index;
   int nb;

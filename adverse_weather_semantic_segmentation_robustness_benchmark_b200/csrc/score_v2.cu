@@ -102,6 +102,15 @@ __device__ __forceinline__ float float_prev(float x) {
   const int b = __float_as_int(x);
   return __int_as_float(x > 0.f ? b - 1 : b + 1);
 }
+// x / T without branches: q0 = RN(x*y), r = RN(x - q0*T) (exact, FMA), q = RN(q0 + r*y) with
+// y = RN(1/T) from the host is the correctly rounded quotient (Markstein) for normal-range operands;
+// tiny / huge |x| (where the residual could underflow or q overflow) take __fdiv_rn.
+__device__ __forceinline__ float div_by_T(float x, float T, float rT) {
+  const float q0 = x * rT;
+  const float r = fmaf(-q0, T, x);
+  return fmaf(r, rT, q0);
+}
+
 // (lo, hi] bin of conf; edges are within an ulp of i/nb so the guess is off by at most one
 __device__ __forceinline__ int ece_bin_fast(float conf, const float* e, int nb) {
   int b = min(max((int)ceilf(conf * (float)nb) - 1, 0), nb - 1);
@@ -163,7 +172,8 @@ __device__ __noinline__ void slow_pixel(const ScoreParams& p, const float* s_edg
 // FADD2/FMUL2/FFMA2 over class pairs; maxima and arg-maxima are scalar (no packed min/max exists).
 //
 // Shared memory: [mbarriers | counters | confusion | edges | per-warp ECE words | AUROC | ring].
-template <int MODE, bool JS, int FAST>
+// DIV: -1 runtime p.div_mode (generic kernels), 0 / 1 compile-time (bins-only kernels).
+template <int MODE, bool JS, int FAST, int DIV>
 __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_constant__ ScoreParams p, const int NU,
                                                                   const float negzero) {
   constexpr bool ENS = MODE != 0;
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
   const float T = p.T;
   const int ignore = p.ignore_index;
   const bool lab_u8 = FAST == 1 || (FAST == 0 && p.label_mode == AWX_LABEL_U8);
-  const int div_mode = p.div_mode;
+  const int div_mode = DIV >= 0 ? DIV : p.div_mode;
   unsigned n_correct = 0, n_bad = 0, n_ambig = 0;
   unsigned u = 0, ph = 0, since_flush = 0;
   unsigned* my_cc = w_cc + warp * nb;
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
         if (ENS) b[ENS ? i : 0] = a[i];
       }
     }
-    if (p.debug_skip) {  // dev: measure the TMA ring alone
+    if (FAST == 0 && p.debug_skip) {  // dev: measure the TMA ring alone (generic kernels only)
       float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < NP; ++i) acc += a[i].x + a[i].y + (ENS ? b[ENS ? i : 0].x + b[ENS ? i : 0].y : 0.f);
@@ -358,7 +368,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
     float vlo = vmax;
     if (div_mode == 1) {
       const float c1 = float_prev(vmax), c2 = float_prev(c1);
-      const float zmax = __fdiv_rn(vmax, T), z1 = __fdiv_rn(c1, T), z2 = __fdiv_rn(c2, T);
+      // branch-free exact quotients; |vmax| outside [1e-25, 1e25] is routed to the scalar slow
+      // path below (residual underflow / quotient overflow), so this block stays straight-line
+      const float zmax = div_by_T(vmax, T, p.rT), z1 = div_by_T(c1, T, p.rT), z2 = div_by_T(c2, T, p.rT);
       vlo = (z1 == zmax) ? ((z2 == zmax) ? c2 : c1) : vmax;
     }
     int arg = 0;
@@ -460,7 +472,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
     o.mpred = marg;
     o.ambig = 0;
     {
-      const bool sane = isfinite(sz) && (!ENS || (isfinite(sa) && isfinite(sb) && isfinite(mi)));
+      const bool range_ok = div_mode != 1 || (fabsf(vmax) > 1e-25f && fabsf(vmax) < 1e25f);
+      const bool sane = range_ok && isfinite(sz) && (!ENS || (isfinite(sa) && isfinite(sb) && isfinite(mi)));
       float conf = __frcp_rn(sz);
       int bin = ece_bin_fast(conf, s_edges, nb);
       if (act && !sane) {
@@ -633,9 +646,9 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
   }
 }
 
-template <int MODE, bool JS, int FAST>
+template <int MODE, bool JS, int FAST, int DIV>
 int launch_v2(const ScoreParams& p, cudaStream_t stream) {
-  auto kern = score_v2_kernel<MODE, JS, FAST>;
+  auto kern = score_v2_kernel<MODE, JS, FAST, DIV>;
   int dev = 0, max_smem = 0;
   AWX_CUDA(cudaGetDevice(&dev));
   AWX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -654,13 +667,20 @@ int launch_v2(const ScoreParams& p, cudaStream_t stream) {
   return AWX_OK;
 }
 
+template <int MODE, int FAST>
+int launch_v2_fast(const ScoreParams& p, cudaStream_t stream) {
+  if (p.div_mode == 0) return launch_v2<MODE, false, FAST, 0>(p, stream);
+  if (p.div_mode == 1) return launch_v2<MODE, false, FAST, 1>(p, stream);
+  return launch_v2<MODE, false, 0, -1>(p, stream);  // exact division everywhere (T <= 0): generic kernel
+}
+
 template <int MODE>
 int launch_v2_mode(const ScoreParams& p, bool js, cudaStream_t stream) {
   const bool maps = p.pred || p.fused || p.conf || p.mi || p.js;
-  if (!maps && p.labels != nullptr && !js)
-    return p.label_mode == AWX_LABEL_U8 ? launch_v2<MODE, false, 1>(p, stream) : launch_v2<MODE, false, 2>(p, stream);
-  if (MODE != 0 && js) return launch_v2<MODE, (MODE != 0), 0>(p, stream);
-  return launch_v2<MODE, false, 0>(p, stream);
+  if (!maps && p.labels != nullptr && !js && !p.debug_skip)
+    return p.label_mode == AWX_LABEL_U8 ? launch_v2_fast<MODE, 1>(p, stream) : launch_v2_fast<MODE, 2>(p, stream);
+  if (MODE != 0 && js) return launch_v2<MODE, (MODE != 0), 0, -1>(p, stream);
+  return launch_v2<MODE, false, 0, -1>(p, stream);
 }
 
 }  // namespace
