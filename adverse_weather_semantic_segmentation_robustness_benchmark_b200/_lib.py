@@ -121,7 +121,8 @@ def load():
         if _lib is not None:
             return _lib
         try:
-            path = _ensure_built()
+            # dev knob: AWX_LIB points at an experimental build of csrc/ (tools/build_variants.py)
+            path = os.environ.get("AWX_LIB") or _ensure_built()
             lib = C.CDLL(path)
         except Exception as exc:  # no fallback: fail loudly
             raise RuntimeError(

@@ -27,6 +27,7 @@ NVCC_FLAGS = [
     "--fmad=true",          # exact paths use __f*_rn intrinsics explicitly
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "-shared",
+    "--threads", "0",       # one ptxas/cicc job per source file
 ]
 
 

@@ -380,8 +380,10 @@ extern "C" int awx_score(const float* logits_a, const float* logits_b, const voi
   p.label_mode = cfg->label_dtype;
   p.ignore_index = cfg->ignore_index;
   p.nb = cfg->ece_bins;
+  p.nbf = (float)cfg->ece_bins;
   p.auroc_bins = ens ? cfg->auroc_bins : 0;
   p.auroc_scale = p.auroc_bins > 0 ? (float)p.auroc_bins / cfg->auroc_hi : 0.f;
+  p.auroc_top = p.auroc_bins > 0 ? (float)(p.auroc_bins - 1) : 0.f;
   p.bins = reinterpret_cast<unsigned long long*>(bins);
   for (int i = 0; i <= cfg->ece_bins; ++i) p.edges[i] = cfg->ece_edges[i];
   bool js = false;

@@ -24,8 +24,10 @@ struct ScoreParams {
   int label_mode;
   int ignore_index;
   int nb;
+  float nbf;     // (float)nb
   int auroc_bins;
   float auroc_scale;
+  float auroc_top;  // (float)(auroc_bins - 1)
   unsigned long long* bins;
   AwxBinsLayout lay;
   void* pred;

@@ -24,13 +24,20 @@ using namespace score_detail;
 namespace {
 
 constexpr int kC = 19;
-constexpr int kTP = 480;                        // pixels per tile (15 consumer warps; 16 warps total -> 128 regs)
-constexpr int kCons = 480;                      // consumer threads (1 px each)
-constexpr int kConsWarps = kCons / 32;
-constexpr int kV2Threads = kCons + 32;          // + producer warp
-constexpr int kUnitFloats = kC * kTP;
-constexpr int kUnitBytes = kUnitFloats * 4;     // 36480
+// Geometry of one kernel variant: CW consumer warps (one pixel per consumer thread) + 1 producer warp.
+//   CW = 15: 512 threads, 128 registers per thread, 36 KB ring units (the generic kernels)
+//   CW = 19: 640 threads,  96 registers per thread, 46 KB ring units (bins-only kernels: more warps to
+//            blend the MUFU / FMA / ALU phases of different warps on each scheduler)
+template <int CW>
+struct Geo {
+  static constexpr int kTP = 32 * CW;            // pixels per tile
+  static constexpr int kCons = kTP;              // consumer threads
+  static constexpr int kThreads = kCons + 32;    // + producer warp
+  static constexpr int kUnitFloats = kC * kTP;
+  static constexpr int kUnitBytes = kUnitFloats * 4;
+};
 constexpr int kMaxUnits = 5;
+constexpr int kSingleWarps = 19;                // consumer warps of the bins-only single-member kernels
 constexpr unsigned kFlushPixels = 60000;        // per-warp ECE words are flushed before 2^16 pixels
 
 typedef unsigned long long u64;
@@ -62,6 +69,11 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsig
                : "memory");
 }
 
+// shared-memory reduction on a 32-bit shared address (no generic -> shared conversion at the use site)
+__device__ __forceinline__ void red_add(uint32_t addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2)
 __device__ __forceinline__ u64& bits(float2& v) { return *reinterpret_cast<u64*>(&v); }
 __device__ __forceinline__ const u64& bits(const float2& v) { return *reinterpret_cast<const u64*>(&v); }
@@ -75,32 +87,25 @@ __device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(bits(d)) : "l"(bits(a)), "l"(bits(b)));
   return d;
 }
-__device__ __forceinline__ float2 sub2(const float2 a, const float2 b) {
-  float2 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(bits(d)) : "l"(bits(a)), "l"(bits(b)));
-  return d;
-}
 __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
   float2 d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(bits(d)) : "l"(bits(a)), "l"(bits(b)), "l"(bits(c)));
   return d;
 }
 __device__ __forceinline__ float2 splat(float x) { return make_float2(x, x); }
-__device__ __forceinline__ float2 max2(const float2 a, const float2 b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
-__device__ __forceinline__ float2 ex2_2(const float2 a) { return make_float2(ex2_approx(a.x), ex2_approx(a.y)); }
-__device__ __forceinline__ float2 lg2_2(const float2 a) { return make_float2(lg2_approx(a.x), lg2_approx(a.y)); }
-__device__ __forceinline__ bool finite2(const float2 a) { return isfinite(a.x) && isfinite(a.y); }
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// largest float below x (finite x)
-__device__ __forceinline__ float float_prev(float x) {
-  if (x == 0.f) return -1.401298464e-45f;
+// the two floats just below x, for finite |x| > 1e-25 (no zero crossing): step the bit pattern
+// towards smaller values (-1 for positive, +1 for negative numbers)
+__device__ __forceinline__ void float_prev2(float x, float& c1, float& c2) {
   const int b = __float_as_int(x);
-  return __int_as_float(x > 0.f ? b - 1 : b + 1);
+  const int s = (b >> 31) | 1;
+  c1 = __int_as_float(b - s);
+  c2 = __int_as_float(b - 2 * s);
 }
 // x / T without branches: q0 = RN(x*y), r = RN(x - q0*T) (exact, FMA), q = RN(q0 + r*y) with
 // y = RN(1/T) from the host is the correctly rounded quotient (Markstein) for normal-range operands;
@@ -120,21 +125,10 @@ __device__ __forceinline__ int ece_bin_fast(float conf, const float* e, int nb) 
 }
 
 // byte offset of the TMA ring inside dynamic shared memory (everything before it is bookkeeping)
-__host__ __device__ inline size_t v2_ring_offset(int nb, int NB) {
+__host__ __device__ inline size_t v2_ring_offset(int cons_warps, int nb, int NB) {
   size_t o = 2 * kMaxUnits * sizeof(u64) + (8 + 368) * 4 + (AWX_MAX_ECE_BINS + 4) * 4;
-  o += (size_t)kConsWarps * nb * 36 + (size_t)2 * NB * 4;
+  o += (size_t)cons_warps * nb * 36 + (size_t)2 * NB * 4;
   return (o + 127) & ~(size_t)127;
-}
-
-// histogram add with a warp-uniform fast path; key < 0 = nothing to add
-__device__ __forceinline__ void hist_add(unsigned* h, int key, int lane) {
-  int same;
-  __match_all_sync(0xffffffffu, key, &same);
-  if (same) {
-    if (lane == 0 && key >= 0) atomicAdd(h + key, 32u);
-  } else if (key >= 0) {
-    atomicAdd(h + key, 1u);
-  }
 }
 
 // Slow path for one pixel straight from global memory (NaN / inf logits): the scalar v1 code.
@@ -162,20 +156,33 @@ __device__ __noinline__ void slow_pixel(const ScoreParams& p, const float* s_edg
 }
 
 // MODE: 0 single member, 1 weighted average, 2 mean.
-// FAST: 0 generic (runtime label dtype, optional per-pixel maps), 1 uint8 labels and bins only,
-//       2 int64 labels and bins only -- the streaming-evaluation configurations, with every
-//       map / dtype branch compiled out.
+// FAST: 0 generic (runtime label dtype, optional per-pixel maps, any edges), 1 uint8 labels and bins
+//       only, 2 int64 labels and bins only -- the streaming-evaluation configurations, with every
+//       map / dtype branch compiled out and the ECE edges known to be linspace(0,1,nb+1).
+// DIV:  -1 runtime p.div_mode (generic kernels), 0 / 1 compile-time (bins-only kernels).
+// CW:   consumer warps (Geo<CW>).
 //
-// Consumer thread t owns pixel t of the 480-pixel tile.  Its 19 class values are held as 10 float2
-// PAIRS OF CLASSES (2i, 2i+1); the 20th slot is a finite "never wins" dummy (-1e30) whose
-// exponentials are exactly 0.  Element-wise work (fusion, x - max, scaling, e*d products) runs on
-// FADD2/FMUL2/FFMA2 over class pairs; maxima and arg-maxima are scalar (no packed min/max exists).
+// Consumer thread t owns pixel t of the tile.  Its 19 class values are held as 10 float2 PAIRS OF
+// CLASSES (2i, 2i+1); the 20th slot is a finite "never wins" dummy (-1e30) whose exponentials are
+// exactly 0.  Element-wise work runs on FADD2/FMUL2/FFMA2 over class pairs; maxima and arg-maxima are
+// scalar (no packed min/max exists).
+//
+// Shifted exponents.  Every softmax is evaluated as e'_c = ex2(fma(x_c, k, -fl(xmax*k))): ONE packed
+// FMA per class pair instead of subtract + multiply.  The rounded product fl(xmax*k) shifts all
+// exponents of a pixel by the same delta = xmax*k - fl(xmax*k) (|delta| <= ulp/2), i.e. e'_c =
+// 2^delta e_c and S' = 2^delta S:
+//   * probabilities e'_c / S' and log2 p_c = t_c - lg2 S' do not see delta at all, so the entropies
+//     H = ln2 (lg2 S' - sum e'_c t_c / S') and the mean probabilities are unchanged;
+//   * the confidence 1/S needs S itself: delta = fma(xmax, k, -fl(xmax*k)) is exact, and
+//     conf = rcp(S') (1 + delta ln2)   (2^delta to first order; delta^2 < 1e-11).
 //
 // Shared memory: [mbarriers | counters | confusion | edges | per-warp ECE words | AUROC | ring].
-// DIV: -1 runtime p.div_mode (generic kernels), 0 / 1 compile-time (bins-only kernels).
-template <int MODE, bool JS, int FAST, int DIV>
-__global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_constant__ ScoreParams p, const int NU,
-                                                                  const float negzero) {
+template <int MODE, bool JS, int FAST, int DIV, int CW>
+__global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
+    score_v2_kernel(const __grid_constant__ ScoreParams p, const int NU, const float negzero) {
+  using G = Geo<CW>;
+  constexpr int kTP = G::kTP, kCons = G::kCons, kConsWarps = CW, kV2Threads = G::kThreads;
+  constexpr int kUnitFloats = G::kUnitFloats;
   constexpr bool ENS = MODE != 0;
   constexpr int NP = (kC + 1) / 2;  // 10 class pairs
   constexpr float kDummy = -1e30f;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
   unsigned* w_lo = w_cc + kConsWarps * nb;
   unsigned* w_hi = w_lo + kConsWarps * nb;
   unsigned* s_auroc = w_hi + kConsWarps * nb;            // [2*NB]
-  float* units = reinterpret_cast<float*>(smem + v2_ring_offset(nb, NB));
+  float* units = reinterpret_cast<float*>(smem + v2_ring_offset(kConsWarps, nb, NB));
   {
     unsigned* w = s_cnt;
     const int words = 8 + 368;
@@ -264,14 +271,18 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
   unsigned* my_cc = w_cc + warp * nb;
   unsigned* my_lo = w_lo + warp * nb;
   unsigned* my_hi = w_hi + warp * nb;
+  const uint32_t conf_sa = smem_u32(s_conf), auroc_sa = smem_u32(s_auroc), cc_sa = smem_u32(my_cc);
+  const uint32_t ece_stride = (uint32_t)(kConsWarps * nb * 4);  // my_cc -> my_lo -> my_hi
   const float* my_units = units + t;
-  long long img = blockIdx.x / tpi, tin = blockIdx.x - img * tpi;
+  // B * HW < 2^32 (score_v2_supported): all pixel and tile indices of the consumers are 32 bit
+  const unsigned HWu = (unsigned)HW, tpiu = (unsigned)tpi, ntu = (unsigned)ntiles;
+  unsigned img = blockIdx.x / tpiu, tin = blockIdx.x - img * tpiu;
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long p0 = tin * kTP;
-    const int npx = (int)((HW - p0) < kTP ? (HW - p0) : kTP);
-    const bool act = t < npx;
-    const long long li = img * HW + p0 + t;
+  for (unsigned tile = blockIdx.x; tile < ntu; tile += gridDim.x) {
+    const unsigned p0 = tin * kTP;
+    const unsigned rem = HWu - p0;
+    const bool act = (unsigned)t < rem;  // rem >= kTP except in the tail tile of an image
+    const unsigned li = img * HWu + p0 + t;
     // label as a 32-bit int; int64 values outside the int range can only be "bad" labels
     int lab = ignore;
     if (have_labels && act) {
@@ -327,8 +338,8 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
       for (int i = 0; i < NP; ++i) acc += a[i].x + a[i].y + (ENS ? b[ENS ? i : 0].x + b[ENS ? i : 0].y : 0.f);
       if (acc == 1234.5678f) n_bad += 1;
       tin += gridDim.x;
-      while (tin >= tpi) {
-        tin -= tpi;
+      while (tin >= tpiu) {
+        tin -= tpiu;
         ++img;
       }
       continue;
@@ -367,9 +378,10 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
     // against the smallest float whose quotient equals the max quotient.
     float vlo = vmax;
     if (div_mode == 1) {
-      const float c1 = float_prev(vmax), c2 = float_prev(c1);
       // branch-free exact quotients; |vmax| outside [1e-25, 1e25] is routed to the scalar slow
       // path below (residual underflow / quotient overflow), so this block stays straight-line
+      float c1, c2;
+      float_prev2(vmax, c1, c2);
       const float zmax = div_by_T(vmax, T, p.rT), z1 = div_by_T(c1, T, p.rT), z2 = div_by_T(c2, T, p.rT);
       vlo = (z1 == zmax) ? ((z2 == zmax) ? c2 : c1) : vmax;
     }
@@ -382,7 +394,7 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
 
     // optional fused-logit output (bit exact: div_mode is 0 or 2 whenever it is requested)
     if (FAST == 0 && p.fused != nullptr && act) {
-      float* fo = p.fused + img * kC * HW + p0 + t;
+      float* fo = p.fused + ((long long)img * kC * HW + p0 + t);
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         fo[(2 * i) * HW] = v[i].x;
@@ -390,122 +402,144 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
       }
     }
 
-    // ---- P3: softmax denominator of the fused logits (dominant term exactly 1)
-    float sz;
+    // ---- P3: softmax denominator of the fused logits (shifted exponents, see header)
+    float sz, zdelta;
     {
+      const float cz = -(vmax * p.kz);
+      zdelta = fmaf(vmax, p.kz, cz) * kLn2;  // exact residual of the rounded product, in nats
       float2 sz2 = splat(0.f);
-      const float2 vm2 = splat(vmax);
+      const float2 cz2 = splat(cz);
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const float2 x = mul2(sub2(v[i], vm2), kz);
+        const float2 x = fma2(v[i], kz, cz2);
         sz2 = add2(sz2, make_float2(ex2_approx(x.x), (2 * i + 1 < kC) ? ex2_approx(x.y) : 0.f));
       }
       sz = sz2.x + sz2.y;
     }
 
-    // ---- members: softmax sums, entropies, mean probabilities
+    // ---- members: softmax sums, entropies, mean probabilities (log2 domain, shifted exponents)
     float mi = 0.f, js = 0.f, sa = 1.f, sb = 1.f;
     int marg = 0;
     if (ENS) {
       float2 sa2 = splat(0.f), sb2 = splat(0.f), ta2 = splat(0.f), tb2 = splat(0.f), xab2 = splat(0.f), xba2 = splat(0.f);
-      const float2 am2 = splat(amax), bm2 = splat(bmax);
+      const float2 ca2 = splat(-(amax * kLog2e)), cb2 = splat(-(bmax * kLog2e));
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const float2 da = sub2(a[i], am2), db = sub2(b[ENS ? i : 0], bm2);
-        const float2 xa = mul2(da, l2e), xb = mul2(db, l2e);
-        const float2 ea = make_float2(ex2_approx(xa.x), (2 * i + 1 < kC) ? ex2_approx(xa.y) : 0.f);
-        const float2 eb = make_float2(ex2_approx(xb.x), (2 * i + 1 < kC) ? ex2_approx(xb.y) : 0.f);
+        const float2 ta = fma2(a[i], l2e, ca2), tb = fma2(b[ENS ? i : 0], l2e, cb2);
+        const float2 ea = make_float2(ex2_approx(ta.x), (2 * i + 1 < kC) ? ex2_approx(ta.y) : 0.f);
+        const float2 eb = make_float2(ex2_approx(tb.x), (2 * i + 1 < kC) ? ex2_approx(tb.y) : 0.f);
         sa2 = add2(sa2, ea);
         sb2 = add2(sb2, eb);
-        ta2 = fma2(ea, da, ta2);
-        tb2 = fma2(eb, db, tb2);
+        ta2 = fma2(ea, ta, ta2);  // sum e'_c t_c
+        tb2 = fma2(eb, tb, tb2);
         if (JS) {
-          xab2 = fma2(ea, db, xab2);
-          xba2 = fma2(eb, da, xba2);
+          xab2 = fma2(ea, tb, xab2);  // sum e'^a_c t^b_c
+          xba2 = fma2(eb, ta, xba2);
         }
         a[i] = ea;
         b[ENS ? i : 0] = eb;
       }
       sa = sa2.x + sa2.y;
       sb = sb2.x + sb2.y;
-      const float ta = ta2.x + ta2.y, tb = tb2.x + tb2.y;
+      const float tsa = ta2.x + ta2.y, tsb = tb2.x + tb2.y;
       const float ra = rcp_approx(sa), rb = rcp_approx(sb);
-      const float2 ka = splat(0.5f * ra), kb = splat(0.5f * rb);
+      // mean probabilities m_c = (e^a_c/Sa + e^b_c/Sb)/2 = ka * u_c with u_c = e^a_c + rho e^b_c
+      const float kas = 0.5f * ra, kbs = 0.5f * rb;
+      const float2 ka = splat(kas), rho = splat(sa * rb);
       float2 hm2 = splat(0.f);
-      float mlm = 0.f, mmax = 0.f;
+      float mlm = 0.f, umax = 0.f;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        const float2 m = fma2(a[i], ka, mul2(b[ENS ? i : 0], kb));
-        const float2 me = add2(m, eps);
-        hm2 = fma2(m, make_float2(lg2_approx(me.x), (2 * i + 1 < kC) ? lg2_approx(me.y) : 0.f), hm2);
+        const float2 uu = fma2(b[ENS ? i : 0], rho, a[i]);
+        const float2 me = fma2(uu, ka, eps);
+        hm2 = fma2(uu, make_float2(lg2_approx(me.x), (2 * i + 1 < kC) ? lg2_approx(me.y) : 0.f), hm2);
         if (JS) {
+          const float2 m = mul2(uu, ka);
           mlm += m.x > 0.f ? m.x * lg2_approx(m.x) : 0.f;
           if (2 * i + 1 < kC) mlm += m.y > 0.f ? m.y * lg2_approx(m.y) : 0.f;
         }
-        a[i] = m;  // keep the mean probabilities for the arg-max below
-        mmax = fmaxf(mmax, fmaxf(m.x, m.y));
+        a[i] = uu;  // keep the (unnormalised) mean probabilities for the arg-max below
+        umax = fmaxf(umax, fmaxf(uu.x, uu.y));
       }
 #pragma unroll
       for (int i = NP - 1; i >= 0; --i) {
-        if (2 * i + 1 < kC) marg = (a[i].y == mmax) ? 2 * i + 1 : marg;
-        marg = (a[i].x == mmax) ? 2 * i : marg;
+        if (2 * i + 1 < kC) marg = (a[i].y == umax) ? 2 * i + 1 : marg;
+        marg = (a[i].x == umax) ? 2 * i : marg;
       }
-      const float lsa = kLn2 * lg2_approx(sa), lsb = kLn2 * lg2_approx(sb);
+      // entropies in bits: H2(p) = lg2 S' - (sum e'_c t_c)/S'; the reference's log(p + eps) adds
+      // -C*eps nats (p >> eps)
+      const float lsa = lg2_approx(sa), lsb = lg2_approx(sb);
+      const float ha2 = lsa - tsa * ra, hb2 = lsb - tsb * rb;
       const float ceps = (float)kC * kEps;
-      const float ha = lsa - ta * ra - ceps;
-      const float hb = lsb - tb * rb - ceps;
-      mi = -kLn2 * (hm2.x + hm2.y) - 0.5f * (ha + hb);
+      mi = kLn2 * (-kas * (hm2.x + hm2.y) - 0.5f * (ha2 + hb2)) + ceps;
       if (JS) {
+        // sum_c m_c lg2 p_c = ka*Ta + kb*Xba - lg2 Sa' ; sum_c m_c lg2 q_c = kb*Tb + ka*Xab - lg2 Sb'
         const float xab = xab2.x + xab2.y, xba = xba2.x + xba2.y;
-        const float kas = 0.5f * ra, kbs = 0.5f * rb;
-        const float mlp = kas * ta + kbs * xba - lsa;
-        const float mlq = kbs * tb + kas * xab - lsb;
-        js = kLn2 * mlm - 0.5f * (mlp + mlq);
+        const float mlp = kas * tsa + kbs * xba - lsa;
+        const float mlq = kbs * tsb + kas * xab - lsb;
+        js = kLn2 * (mlm - 0.5f * (mlp + mlq));
       }
     }
 
     // ---- confidence, ECE bin, slow paths
-    PixOut o;
-    o.pred = arg;
-    o.mi = mi;
-    o.js = js;
-    o.mpred = marg;
-    o.ambig = 0;
+    int pred = arg, bin, ambig = 0;
+    float conf;
     {
       const bool range_ok = div_mode != 1 || (fabsf(vmax) > 1e-25f && fabsf(vmax) < 1e25f);
-      const bool sane = range_ok && isfinite(sz) && (!ENS || (isfinite(sa) && isfinite(sb) && isfinite(mi)));
-      float conf = __frcp_rn(sz);
-      int bin = ece_bin_fast(conf, s_edges, nb);
-      if (act && !sane) {
-        const float* ga = p.a + img * kC * HW + p0 + t;
-        slow_pixel<ENS, JS>(p, s_edges, ga, ENS ? p.b + img * kC * HW + p0 + t : nullptr, o);
+      // one finiteness test: every term is >= 1 or tiny, so the sum is non-finite iff a term is
+      const float chk = ENS ? (sz + sa) + (sb + mi) : sz;
+      const bool sane = range_ok && fabsf(chk) < 3e38f;
+      const float r = __frcp_rn(sz);
+      conf = fminf(fmaf(r, zdelta, r), 1.f);
+      bool near;
+      if (FAST != 0) {
+        // edges are linspace(0,1,nb+1) (checked by the host): bin = ceil(conf*nb) - 1 unless conf is
+        // within ~18 ulp of an edge, and those pixels take the fp64 path against the real edges
+        const float s = conf * p.nbf;
+        const float tt = s + 12582912.f;  // 1.5 * 2^23: round to nearest integer
+        const int j = __float_as_int(tt) - 0x4b400000;
+        const float d = s - (tt - 12582912.f);
+        bin = min(j - (d < 0.f ? 1 : 0), nb - 1);
+        near = fabsf(d) <= s * 2.4e-6f && j < nb;
       } else {
-        if (act && bin >= 0) {
+        bin = ece_bin_fast(conf, s_edges, nb);
+        near = false;
+        if (bin >= 0) {
           const float tol = conf * 1.9e-6f;  // 16 ulp
-          const bool near_lo = bin > 0 && (conf - s_edges[bin]) <= tol;
-          const bool near_hi = bin < nb - 1 && (s_edges[bin + 1] - conf) <= tol;
-          if (near_lo || near_hi) {
-            const float* ga = p.a + img * kC * HW + p0 + t;
-            conf = exact_confidence(ga, ENS ? p.b + img * kC * HW + p0 + t : nullptr, HW, kC, MODE == 2, p.w0, p.w1,
-                                    div_mode, T, s_edges, nb, &o.ambig);
-            bin = ece_bin_fast(conf, s_edges, nb);
-          }
+          near = (bin > 0 && (conf - s_edges[bin]) <= tol) || (bin < nb - 1 && (s_edges[bin + 1] - conf) <= tol);
         }
-        o.conf = conf;
-        o.bin = bin;
+      }
+      if (act && (!sane || near)) {
+        const long long go = (long long)img * kC * HW + p0 + t;
+        const float* ga = p.a + go;
+        const float* gb = ENS ? p.b + go : nullptr;
+        if (!sane) {
+          PixOut so;
+          slow_pixel<ENS, JS>(p, s_edges, ga, gb, so);
+          pred = so.pred;
+          conf = so.conf;
+          bin = so.bin;
+          ambig = so.ambig;
+          mi = so.mi;
+          js = so.js;
+          marg = so.mpred;
+        } else {
+          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, p.w0, p.w1, div_mode, T, s_edges, nb, &ambig);
+          bin = ece_bin(conf, s_edges, nb);
+        }
       }
     }
 
     if (FAST == 0 && act) {
       if (p.pred) {
         if (p.pred_dtype == AWX_PRED_U8)
-          static_cast<uint8_t*>(p.pred)[li] = (uint8_t)o.pred;
+          static_cast<uint8_t*>(p.pred)[li] = (uint8_t)pred;
         else
-          static_cast<long long*>(p.pred)[li] = o.pred;
+          static_cast<long long*>(p.pred)[li] = pred;
       }
-      if (p.conf) p.conf[li] = o.conf;
-      if (ENS && p.mi) p.mi[li] = o.mi;
-      if (ENS && JS && p.js) p.js[li] = o.js;
+      if (p.conf) p.conf[li] = conf;
+      if (ENS && p.mi) p.mi[li] = mi;
+      if (ENS && JS && p.js) p.js[li] = js;
     }
 
     // ---- statistics
@@ -524,26 +558,26 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
       }
       since_flush += 32u;
       const bool valid = act && lab != ignore;
-      const bool correct = valid && lab == o.pred;
+      const bool correct = valid && lab == pred;
       n_correct += correct;
       int ckey = -1, akey = -1;
       if (valid) {
         // confusion index as torch evaluates targets*C + predictions (uint8 product wraps mod 256)
-        const int idx = (lab_u8 ? ((lab * kC) & 0xff) : lab * kC) + o.pred;
+        const int idx = (lab_u8 ? ((lab * kC) & 0xff) : lab * kC) + pred;
         const bool inside = lab_u8 ? (idx < kC * kC) : (lab >= 0 && lab < kC);
         if (inside)
           ckey = idx;
         else
           ++n_bad;
-        n_ambig += o.ambig;
+        n_ambig += ambig;
         if (ENS && NB > 0) {
-          float qv = floorf(o.mi * p.auroc_scale);
-          qv = is_nan(qv) ? 0.f : qv;
-          akey = (lab != o.mpred ? 0 : NB) + (int)fminf(fmaxf(qv, 0.f), (float)(NB - 1));
+          // floor(mi * scale) clamped to [0, NB-1]; NaN -> 0 (fmaxf returns the non-NaN operand)
+          const float qv = fminf(fmaxf(mi * p.auroc_scale, 0.f), p.auroc_top);
+          akey = (lab != marg ? 0 : NB) + (int)qv;
         }
       }
-      const int bin = valid ? o.bin : -1;
-      const unsigned fx = bin >= 0 ? __float2uint_rz(o.conf * 2147483648.f) : 0u;
+      if (!valid) bin = -1;
+      const unsigned fx = bin >= 0 ? __float2uint_rz(conf * 2147483648.f) : 0u;
       // one warp-uniformity test for all three histograms (piecewise-constant real data)
       const int key = (ckey + 1) | ((akey + 1) << 9) | ((bin + 1) << 23);
       int same;
@@ -553,28 +587,30 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
           const unsigned lo = __reduce_add_sync(0xffffffffu, fx & 0xffffu);
           const unsigned hi = __reduce_add_sync(0xffffffffu, fx >> 16);
           if (lane == 0) {
-            if (ckey >= 0) atomicAdd(s_conf + ckey, 32u);
-            if (akey >= 0) atomicAdd(s_auroc + akey, 32u);
+            if (ckey >= 0) red_add(conf_sa + 4u * ckey, 32u);
+            if (akey >= 0) red_add(auroc_sa + 4u * akey, 32u);
             if (bin >= 0) {
-              atomicAdd(my_cc + bin, 32u | (correct ? (32u << 16) : 0u));
-              atomicAdd(my_lo + bin, lo);
-              atomicAdd(my_hi + bin, hi);
+              const uint32_t ba = cc_sa + 4u * bin;
+              red_add(ba, 32u | (correct ? (32u << 16) : 0u));
+              red_add(ba + ece_stride, lo);
+              red_add(ba + 2u * ece_stride, hi);
             }
           }
         }
       } else {
-        if (ckey >= 0) atomicAdd(s_conf + ckey, 1u);
-        if (akey >= 0) atomicAdd(s_auroc + akey, 1u);
+        if (ckey >= 0) red_add(conf_sa + 4u * ckey, 1u);
+        if (akey >= 0) red_add(auroc_sa + 4u * akey, 1u);
         if (bin >= 0) {
-          atomicAdd(my_cc + bin, 1u | (correct ? 0x10000u : 0u));
-          atomicAdd(my_lo + bin, fx & 0xffffu);
-          atomicAdd(my_hi + bin, fx >> 16);
+          const uint32_t ba = cc_sa + 4u * bin;
+          red_add(ba, 1u | (correct ? 0x10000u : 0u));
+          red_add(ba + ece_stride, fx & 0xffffu);
+          red_add(ba + 2u * ece_stride, fx >> 16);
         }
       }
     }
     tin += gridDim.x;
-    while (tin >= tpi) {
-      tin -= tpi;
+    while (tin >= tpiu) {
+      tin -= tpiu;
       ++img;
     }
   }
@@ -646,41 +682,62 @@ __global__ void __launch_bounds__(kV2Threads, 1) score_v2_kernel(const __grid_co
   }
 }
 
-template <int MODE, bool JS, int FAST, int DIV>
+template <int MODE, bool JS, int FAST, int DIV, int CW>
 int launch_v2(const ScoreParams& p, cudaStream_t stream) {
-  auto kern = score_v2_kernel<MODE, JS, FAST, DIV>;
+  using G = Geo<CW>;
+  auto kern = score_v2_kernel<MODE, JS, FAST, DIV, CW>;
   int dev = 0, max_smem = 0;
   AWX_CUDA(cudaGetDevice(&dev));
   AWX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t fixed = v2_ring_offset(p.nb, p.auroc_bins);
-  int nu = (int)(((size_t)max_smem - fixed) / kUnitBytes);
+  const size_t fixed = v2_ring_offset(CW, p.nb, p.auroc_bins);
+  int nu = (int)(((size_t)max_smem - fixed) / G::kUnitBytes);
   if (nu > kMaxUnits) nu = kMaxUnits;
   AWX_REQUIRE(nu >= 2, AWX_E_UNSUPPORTED, "awx_score v2: histograms leave no room for the TMA ring");
-  const size_t smem = (size_t)nu * kUnitBytes + fixed;
+  const size_t smem = (size_t)nu * G::kUnitBytes + fixed;
   AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long ntiles = p.B * ((p.HW + kTP - 1) / kTP);
+  const long long ntiles = p.B * ((p.HW + G::kTP - 1) / G::kTP);
   long long blocks = sm_count();
   if (blocks > ntiles) blocks = ntiles;
-  kern<<<(unsigned)blocks, kV2Threads, smem, stream>>>(p, nu, -0.0f);
+  kern<<<(unsigned)blocks, G::kThreads, smem, stream>>>(p, nu, -0.0f);
   AWX_CUDA(cudaGetLastError());
   note_launch();
   return AWX_OK;
 }
 
+// bins-only kernels: compile-time division mode; the single-member kernels (fewer live registers) run
+// 19 consumer warps.  AWX_V2_WARPS=15|19 overrides for A/B measurements.
 template <int MODE, int FAST>
 int launch_v2_fast(const ScoreParams& p, cudaStream_t stream) {
-  if (p.div_mode == 0) return launch_v2<MODE, false, FAST, 0>(p, stream);
-  if (p.div_mode == 1) return launch_v2<MODE, false, FAST, 1>(p, stream);
-  return launch_v2<MODE, false, 0, -1>(p, stream);  // exact division everywhere (T <= 0): generic kernel
+  static const int cw = [] {
+    const char* e = getenv("AWX_V2_WARPS");
+    return (e && atoi(e) == 15) ? 15 : (e && atoi(e) == 19) ? 19 : kSingleWarps;
+  }();
+  if (p.div_mode == 2) return launch_v2<MODE, false, 0, -1, 15>(p, stream);  // exact division everywhere (T <= 0)
+  if constexpr (MODE == 0) {
+    if (cw == 19)
+      return p.div_mode == 0 ? launch_v2<MODE, false, FAST, 0, 19>(p, stream) : launch_v2<MODE, false, FAST, 1, 19>(p, stream);
+  }
+  return p.div_mode == 0 ? launch_v2<MODE, false, FAST, 0, 15>(p, stream) : launch_v2<MODE, false, FAST, 1, 15>(p, stream);
+}
+
+// edges within 2 ulp of j/nb (what torch.linspace(0, 1, nb + 1) produces): the bins-only kernels
+// classify without looking the edges up
+bool uniform_edges(const ScoreParams& p) {
+  if (p.edges[0] != 0.f || p.edges[p.nb] != 1.f) return false;
+  for (int j = 1; j < p.nb; ++j) {
+    const double want = (double)j / (double)p.nb;
+    if (fabs((double)p.edges[j] - want) > 2.4e-7 * want) return false;
+  }
+  return true;
 }
 
 template <int MODE>
 int launch_v2_mode(const ScoreParams& p, bool js, cudaStream_t stream) {
   const bool maps = p.pred || p.fused || p.conf || p.mi || p.js;
-  if (!maps && p.labels != nullptr && !js && !p.debug_skip)
+  if (!maps && p.labels != nullptr && !js && !p.debug_skip && uniform_edges(p))
     return p.label_mode == AWX_LABEL_U8 ? launch_v2_fast<MODE, 1>(p, stream) : launch_v2_fast<MODE, 2>(p, stream);
-  if (MODE != 0 && js) return launch_v2<MODE, (MODE != 0), 0, -1>(p, stream);
-  return launch_v2<MODE, false, 0, -1>(p, stream);
+  if (MODE != 0 && js) return launch_v2<MODE, (MODE != 0), 0, -1, 15>(p, stream);
+  return launch_v2<MODE, false, 0, -1, 15>(p, stream);
 }
 
 }  // namespace
