@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   // B * HW < 2^32 (score_v2_supported): all pixel and tile indices of the consumers are 32 bit
   const unsigned HWu = (unsigned)HW, tpiu = (unsigned)tpi, ntu = (unsigned)ntiles;
   unsigned img = blockIdx.x / tpiu, tin = blockIdx.x - img * tpiu;
+  const unsigned step_img = gridDim.x / tpiu, step_tin = gridDim.x - step_img * tpiu;
 
   for (unsigned tile = blockIdx.x; tile < ntu; tile += gridDim.x) {
     const unsigned p0 = tin * kTP;
@@ -325,13 +326,8 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         ph ^= 1u;
       }
     }
-    if (!act) {  // tail tile: stale ring contents stand in for this lane; neutralise them
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        a[i] = make_float2(0.f, (2 * i + 1 < kC) ? 0.f : kDummy);
-        if (ENS) b[ENS ? i : 0] = a[i];
-      }
-    }
+    // Tail tile: lanes past the end of the image compute on stale ring contents; nothing they produce
+    // is stored or counted (every store, slow path and histogram update below is guarded by act).
     if (FAST == 0 && p.debug_skip) {  // dev: measure the TMA ring alone (generic kernels only)
       float acc = 0.f;
 #pragma unroll
@@ -489,7 +485,8 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       // one finiteness test: every term is >= 1 or tiny, so the sum is non-finite iff a term is
       const float chk = ENS ? (sz + sa) + (sb + mi) : sz;
       const bool sane = range_ok && fabsf(chk) < 3e38f;
-      const float r = __frcp_rn(sz);
+      const float r0 = rcp_approx(sz);
+      const float r = fmaf(r0, fmaf(-sz, r0, 1.f), r0);  // one Newton step: <= 1 ulp
       conf = fminf(fmaf(r, zdelta, r), 1.f);
       bool near;
       if (FAST != 0) {
@@ -608,8 +605,9 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         }
       }
     }
-    tin += gridDim.x;
-    while (tin >= tpiu) {
+    tin += step_tin;
+    img += step_img;
+    if (tin >= tpiu) {
       tin -= tpiu;
       ++img;
     }
