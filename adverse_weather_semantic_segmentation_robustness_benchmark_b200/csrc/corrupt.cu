@@ -158,22 +158,38 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
 }
 
 // --------------------------------------------------------------------------- rain / snow
+// One CTA filters a 16 x 128 pixel tile.  Everything is indexed in ELEMENTS (bytes of the HWC row: 3 per
+// pixel), because both filter passes work per channel and an element's neighbours are 3 elements away.
+//   stage 1  load.  A thread takes a UNIT of 16 pixels = 48 bytes = three 16-byte loads (units start
+//            at multiples of 16 pixels, so they are pixel aligned AND 16-byte aligned), converts through
+//            the u8 -> fp32 table, applies the point operation and the overlay bit (one mask word
+//            covers the unit) and writes 12 float4 to s_pre.  The tile needs R <= 3 halo pixels on each
+//            side; it stages one whole unit per side (rows: BORDER_REFLECT_101 on the row index;
+//            columns: units that are not fully inside the image take the per-pixel path).
+//   stage 2  horizontal pass, register blocked: a thread produces 12 consecutive elements of one row
+//            from 5 (R=1) or 9 (R=3) float4 loads of s_pre -> s_h (3 float4 stores).
+//   stage 3  vertical pass, register blocked: a thread owns 4 adjacent element columns and 8 output
+//            rows: 8 + 2R float4 loads of s_h, then clip * 255, truncate, one 32-bit store per row
+//            (a warp writes 128 contiguous bytes).
+// Shared-memory traffic per output element drops from 14 scalar loads to ~1.3 vector accesses.
+constexpr int kUnitPx = 16;                          // pixels per load unit
+constexpr int kPreW = (kTileW + 2 * kUnitPx) * 3 + 4;  // s_pre row: tile + one unit of halo per side, +4 so that
+                                                      // 4 consecutive rows start 4 banks apart (elements)
+constexpr int kRowE = kTileW * 3;                    // output elements per tile row
+constexpr int kHBlock = 12;                          // elements per horizontal-pass task
+
 template <int R>
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
                                                              const AwxCorruptParams* __restrict__ params,
                                                              const unsigned* __restrict__ mask, int H, int W, int WW) {
-  constexpr int PW = kTileW + 2 * R;  // haloed tile width in pixels
   constexpr int PH = kTileH + 2 * R;
-  constexpr int PRE_STRIDE = PW * 3;
-  constexpr int ROW = kTileW * 3;
   const int b = blockIdx.z;
   const AwxCorruptParams prm = params[b];
   if ((prm.kind != AWX_RAIN && prm.kind != AWX_SNOW) || prm.blur_k != 2 * R + 1) return;
 
   extern __shared__ __align__(16) unsigned char smem[];
-  float* s_pre = reinterpret_cast<float*>(smem);      // [PH][PW*3] point-op'ed, overlaid, fp32
-  float* s_h = s_pre + PH * PRE_STRIDE;               // [PH][kTileW*3] after the horizontal pass
-  uint8_t* s_o = reinterpret_cast<uint8_t*>(s_h + PH * ROW);  // [kTileH][kTileW*3]
+  float* s_pre = reinterpret_cast<float*>(smem);  // [PH][kPreW] point-op'ed, overlaid, fp32
+  float* s_h = s_pre + PH * kPreW;                // [PH][kRowE] after the horizontal pass
   __shared__ float s_unit[256];
   build_unit_table(s_unit);
   __syncthreads();
@@ -184,82 +200,152 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   const unsigned* m = mask + (size_t)b * H * WW;
   const bool rain = prm.kind == AWX_RAIN;
   const float k1 = prm.f0, k2 = prm.f1;  // rain: x*k1 + k2 ; snow: clip(x + k1)
+  const bool vec_ok = ((W * 3) & 15) == 0 && (((uintptr_t)src) & 15) == 0;
 
-  // ---- stage 1: load (reflect-101), point op, overlay -> s_pre
-  for (int i = threadIdx.x; i < PH * PW; i += kBlurThreads) {
-    const int ry = i / PW, rx = i - ry * PW;
+  auto point = [&](unsigned u8, int c, bool over) -> float {
+    const float x = s_unit[u8];
+    if (rain) {
+      const float v = __fadd_rn(__fmul_rn(x, k1), k2);
+      return over ? (c == 0 ? 0.8f : (c == 1 ? 0.9f : 1.0f)) : v;
+    }
+    const float v = fminf(fmaxf(__fadd_rn(x, k1), 0.0f), 1.0f);
+    return over ? 1.0f : v;
+  };
+
+  // ---- stage 1: load units, point op, overlay -> s_pre
+  // task order: 4 rows x UPR units per group, rows fastest, so that a quarter warp (4 rows x 2 units)
+  // writes 8 distinct 16-byte bank groups and a warp still reads 8 consecutive units of each row
+  constexpr int UPR = kTileW / kUnitPx + 2;  // units per staged row
+  for (int i = threadIdx.x; i < ((PH + 3) / 4) * 4 * UPR; i += kBlurThreads) {
+    const int grp = i / (4 * UPR), j = i - grp * (4 * UPR);
+    const int ry = grp * 4 + (j & 3), un = j >> 2;
+    if (ry >= PH) continue;
     const int sy = reflect101(y0 + ry - R, H);
-    const int sx = reflect101(x0 + rx - R, W);
-    const bool over = (m[(size_t)sy * WW + (sx >> 5)] >> (sx & 31)) & 1u;
-    const uint8_t* px = src + ((size_t)sy * W + sx) * 3;
-    float* o = s_pre + ry * PRE_STRIDE + rx * 3;
+    const int ux = x0 + (un - 1) * kUnitPx;  // first pixel of the unit (may be outside the image)
+    float* o = s_pre + ry * kPreW + un * (kUnitPx * 3);
+    if (vec_ok && ux >= 0 && ux + kUnitPx <= W) {
+      const uint8_t* g = src + ((size_t)sy * W + ux) * 3;
+      const unsigned mw = m[(size_t)sy * WW + (ux >> 5)] >> (ux & 31);  // bit j = pixel ux + j
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float x = s_unit[px[c]];
-      float v;
-      if (rain) {
-        v = __fadd_rn(__fmul_rn(x, k1), k2);
-        if (over) v = c == 0 ? 0.8f : (c == 1 ? 0.9f : 1.0f);
-      } else {
-        v = fminf(fmaxf(__fadd_rn(x, k1), 0.0f), 1.0f);
-        if (over) v = 1.0f;
+      for (int q = 0; q < 3; ++q) {
+        const uint4 w = ld_stream_u4(g + 16 * q);
+        const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int e = 16 * q + k;  // element within the unit: pixel e / 3, channel e % 3
+          f[k] = point((ws[k >> 2] >> ((k & 3) * 8)) & 0xffu, e % 3, (mw >> (e / 3)) & 1u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          reinterpret_cast<float4*>(o + 16 * q)[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
       }
-      o[c] = v;
-    }
-  }
-  __syncthreads();
-  // ---- stage 2: horizontal pass
-  const float t0 = prm.taps[0], t1 = prm.taps[1], t2 = prm.taps[2], t3 = prm.taps[3];
-  for (int i = threadIdx.x; i < PH * ROW; i += kBlurThreads) {
-    const int ry = i / ROW, col = i - ry * ROW;
-    const float* p = s_pre + ry * PRE_STRIDE + col + 3 * R;
-    float v;
-    if (R == 1) {
-      v = p[0] * t0 + (p[-3] + p[3]) * t1;
     } else {
-      // generic row filter order: leftmost tap first
-      v = p[-9] * t3;
-      v += p[-6] * t2;
-      v += p[-3] * t1;
-      v += p[0] * t0;
-      v += p[3] * t1;
-      v += p[6] * t2;
-      v += p[9] * t3;
+      // image border / unaligned rows: per pixel, only the pixels the filter can reach
+      for (int j = 0; j < kUnitPx; ++j) {
+        const int xx = ux + j;
+        if (xx < x0 - R || xx >= x0 + kTileW + R) continue;
+        const int sx = reflect101(xx, W);
+        const bool over = (m[(size_t)sy * WW + (sx >> 5)] >> (sx & 31)) & 1u;
+        const uint8_t* px = src + ((size_t)sy * W + sx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[j * 3 + c] = point(px[c], c, over);
+      }
     }
-    s_h[i] = v;
   }
   __syncthreads();
-  // ---- stage 3: vertical pass (symmetric pairing), clip, scale, truncate
-  for (int i = threadIdx.x; i < kTileH * ROW; i += kBlurThreads) {
-    const int ry = i / ROW, col = i - ry * ROW;
-    const float* p = s_h + (ry + R) * ROW + col;
-    float v = p[0] * t0 + (p[-ROW] + p[ROW]) * t1;
-    if (R == 3) {
-      v += (p[-2 * ROW] + p[2 * ROW]) * t2;
-      v += (p[-3 * ROW] + p[3 * ROW]) * t3;
+
+  // ---- stage 2: horizontal pass (12 elements per task)
+  const float t0 = prm.taps[0], t1 = prm.taps[1], t2 = prm.taps[2], t3 = prm.taps[3];
+  constexpr int HB = kRowE / kHBlock;  // 32 tasks per row
+  // output element col <-> s_pre element kUnitPx*3 + col; taps reach 3R elements either way.
+  // first float4 that covers element 48 + col0 - 3R (col0 a multiple of 12): 36 + col0 (R=3), 44 + col0 (R=1)
+  constexpr int LEAD = R == 3 ? 3 : 1;     // elements loaded before the first one needed
+  constexpr int NV = R == 3 ? 9 : 5;       // float4 loads per task (12 + 6R elements after LEAD)
+  constexpr int BASE = kUnitPx * 3 - 3 * R - LEAD;
+  for (int i = threadIdx.x; i < PH * HB; i += kBlurThreads) {
+    const int ry = i / HB, blk = i - ry * HB;
+    const float4* pv = reinterpret_cast<const float4*>(s_pre + ry * kPreW + BASE + blk * kHBlock);
+    float w[4 * NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float4 q = pv[k];
+      w[4 * k] = q.x;
+      w[4 * k + 1] = q.y;
+      w[4 * k + 2] = q.z;
+      w[4 * k + 3] = q.w;
     }
-    s_o[i] = (uint8_t)to_u8_f32(v);
+    float r[kHBlock];
+#pragma unroll
+    for (int e = 0; e < kHBlock; ++e) {
+      const float* p = w + LEAD + 3 * R + e;  // centre tap
+      float v;
+      if (R == 1) {
+        v = p[0] * t0 + (p[-3] + p[3]) * t1;
+      } else {
+        // generic row filter order: leftmost tap first
+        v = p[-9] * t3;
+        v += p[-6] * t2;
+        v += p[-3] * t1;
+        v += p[0] * t0;
+        v += p[3] * t1;
+        v += p[6] * t2;
+        v += p[9] * t3;
+      }
+      r[e] = v;
+    }
+    float4* ov = reinterpret_cast<float4*>(s_h + ry * kRowE + blk * kHBlock);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ov[k] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
   }
   __syncthreads();
-  // ---- stage 4: store
-  const int tw = min(kTileW, W - x0), th = min(kTileH, H - y0);
-  const bool vec = tw == kTileW && (((uintptr_t)(dst + ((size_t)y0 * W + x0) * 3)) & 15) == 0 && ((W * 3) & 15) == 0;
-  if (vec) {
-    for (int i = threadIdx.x; i < th * (ROW / 16); i += kBlurThreads) {
-      const int ry = i / (ROW / 16), q = i - ry * (ROW / 16);
-      st_stream_u4(dst + ((size_t)(y0 + ry) * W + x0) * 3 + q * 16, reinterpret_cast<const uint4*>(s_o + ry * ROW)[q]);
-    }
-  } else {
-    for (int i = threadIdx.x; i < th * tw * 3; i += kBlurThreads) {
-      const int ry = i / (tw * 3), col = i - ry * (tw * 3);
-      dst[((size_t)(y0 + ry) * W + x0) * 3 + col] = s_o[ry * ROW + col];
+
+  // ---- stage 3: vertical pass (4 columns x 8 rows per task), clip, scale, truncate, store
+  const int tw3 = min(kTileW, W - x0) * 3, th = min(kTileH, H - y0);
+  constexpr int CG = kRowE / 4;  // 96 column groups
+  constexpr int VR = 8;          // output rows per task
+  const bool st32 = ((W * 3) & 3) == 0 && (((uintptr_t)dst) & 3) == 0;
+  for (int i = threadIdx.x; i < CG * (kTileH / VR); i += kBlurThreads) {
+    const int half = i / CG, cg = i - half * CG;
+    const float4* pv = reinterpret_cast<const float4*>(s_h + (half * VR) * kRowE + cg * 4);
+    float4 win[VR + 2 * R];
+#pragma unroll
+    for (int k = 0; k < VR + 2 * R; ++k) win[k] = pv[k * (kRowE / 4)];
+#pragma unroll
+    for (int rr = 0; rr < VR; ++rr) {
+      const int ry = half * VR + rr;
+      if (ry >= th) break;
+      auto vfilt = [&](float c0, float m1, float p1, float m2, float p2, float m3, float p3) -> unsigned {
+        float v = c0 * t0 + (m1 + p1) * t1;
+        if (R == 3) {
+          v += (m2 + p2) * t2;
+          v += (m3 + p3) * t3;
+        }
+        return to_u8_f32(v);
+      };
+      const float4 c = win[rr + R], a1 = win[rr + R - 1], b1 = win[rr + R + 1];
+      const float4 a2 = win[R == 3 ? rr + R - 2 : 0], b2 = win[R == 3 ? rr + R + 2 : 0];
+      const float4 a3 = win[R == 3 ? rr + R - 3 : 0], b3 = win[R == 3 ? rr + R + 3 : 0];
+      const unsigned o0 = vfilt(c.x, a1.x, b1.x, a2.x, b2.x, a3.x, b3.x);
+      const unsigned o1 = vfilt(c.y, a1.y, b1.y, a2.y, b2.y, a3.y, b3.y);
+      const unsigned o2 = vfilt(c.z, a1.z, b1.z, a2.z, b2.z, a3.z, b3.z);
+      const unsigned o3 = vfilt(c.w, a1.w, b1.w, a2.w, b2.w, a3.w, b3.w);
+      uint8_t* d = dst + ((size_t)(y0 + ry) * W + x0) * 3 + cg * 4;
+      if (st32 && cg * 4 + 3 < tw3) {
+        *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+      } else {
+        const unsigned ob[4] = {o0, o1, o2, o3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (cg * 4 + k < tw3) d[k] = (uint8_t)ob[k];
+      }
     }
   }
 }
 
 template <int R>
 constexpr size_t blur_smem() {
-  return (size_t)(kTileH + 2 * R) * ((kTileW + 2 * R) * 3 + kTileW * 3) * sizeof(float) + (size_t)kTileH * kTileW * 3;
+  return (size_t)(kTileH + 2 * R) * (kPreW + kRowE) * sizeof(float);
 }
 
 template <int R>
