@@ -74,6 +74,12 @@ __device__ __forceinline__ void red_add(uint32_t addr, unsigned v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// the same, predicated on key >= 0 inside the instruction (no branch / reconvergence around it)
+__device__ __forceinline__ void red_add_if(int key, uint32_t addr, unsigned v) {
+  asm volatile("{\n .reg .pred p;\n setp.ge.s32 p, %0, 0;\n @p red.shared.add.u32 [%1], %2;\n}" ::"r"(key), "r"(addr), "r"(v)
+               : "memory");
+}
+
 // ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2)
 __device__ __forceinline__ u64& bits(float2& v) { return *reinterpret_cast<u64*>(&v); }
 __device__ __forceinline__ const u64& bits(const float2& v) { return *reinterpret_cast<const u64*>(&v); }
@@ -595,14 +601,12 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
           }
         }
       } else {
-        if (ckey >= 0) red_add(conf_sa + 4u * ckey, 1u);
-        if (akey >= 0) red_add(auroc_sa + 4u * akey, 1u);
-        if (bin >= 0) {
-          const uint32_t ba = cc_sa + 4u * bin;
-          red_add(ba, 1u | (correct ? 0x10000u : 0u));
-          red_add(ba + ece_stride, fx & 0xffffu);
-          red_add(ba + 2u * ece_stride, fx >> 16);
-        }
+        red_add_if(ckey, conf_sa + 4u * ckey, 1u);
+        red_add_if(akey, auroc_sa + 4u * akey, 1u);
+        const uint32_t ba = cc_sa + 4u * bin;
+        red_add_if(bin, ba, 1u | (correct ? 0x10000u : 0u));
+        red_add_if(bin, ba + ece_stride, fx & 0xffffu);
+        red_add_if(bin, ba + 2u * ece_stride, fx >> 16);
       }
     }
     tin += step_tin;
