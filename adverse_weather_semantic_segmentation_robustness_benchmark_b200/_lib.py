@@ -23,7 +23,7 @@ FUSE_SINGLE, FUSE_WEIGHTED, FUSE_MAXCONF, FUSE_MEAN = 0, 1, 2, 3
 LABEL_U8, LABEL_I64 = 0, 1
 PRED_U8, PRED_I64 = 0, 1
 CLEAN, FOG, RAIN, SNOW, NIGHT = 0, 1, 2, 3, 4
-F32, F64 = 0, 1
+F32, F64, BF16, U8 = 0, 1, 2, 3
 KIND_CODES = {"clean": CLEAN, "fog": FOG, "rain": RAIN, "snow": SNOW, "night": NIGHT}
 
 CNT_VALID, CNT_CORRECT, CNT_BAD_LABEL, CNT_ECE_AMBIG, CNT_ENS_WRONG, CNT_PICK_AMBIG, CNT_NO_BIN, CNT_PIXELS = range(8)
@@ -85,6 +85,20 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "awx_fogloss_workspace_bytes": (C.c_size_t, []),
     "awx_scale_inplace": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "awx_normalize_chw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "awx_style_transfer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_double, C.c_int32,
+                                     C.c_void_p]),
+    "awx_temperature_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "awx_temperature_nll": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "awx_fog_density_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "awx_local_contrast": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
+                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "awx_fog_density_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                         C.c_void_p, C.c_void_p]),
+    "awx_estimate_depth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                     C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lock = threading.Lock()

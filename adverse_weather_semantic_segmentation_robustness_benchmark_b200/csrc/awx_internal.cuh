@@ -31,6 +31,8 @@ int cuda_fail(cudaError_t e, const char* where);
   } while (0)
 
 int sm_count();
+int launch_gauss_f64(const double* in, void* out, int32_t out_dtype, double* tmp, int64_t batch, int32_t H, int32_t W,
+                     double ramp_scale, double floor_value, const double* weights /*HOST*/, int32_t radius, cudaStream_t s);
 void note_launch(int n = 1);  // counts kernels launched by this library (awx_launch_count)
 
 // --------------------------------------------------------------------- device helpers

@@ -377,7 +377,7 @@ struct GaussTaps {
 
 template <bool VERTICAL, typename OT>
 __global__ void __launch_bounds__(256) depth_pass_kernel(const double* __restrict__ in, OT* __restrict__ out, int H, int W,
-                                                          long long total, const GaussTaps taps, double scale) {
+                                                          long long total, const GaussTaps taps, double scale, double floor_value) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % W);
     const long long t = i / W;
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256) depth_pass_kernel(const double* __restric
       }
       acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(lo, hi), taps.w[j]));
     }
-    if (!VERTICAL) acc = fmax(acc, 1.0);  // np.maximum(depth, 1.0)
+    if (!VERTICAL) acc = fmax(acc, floor_value);  // np.maximum(depth, 1.0) for the synthetic depth; -inf: none
     out[i] = (OT)acc;
   }
 }
@@ -480,13 +480,11 @@ extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int3
   return AWX_OK;
 }
 
-extern "C" int awx_synth_depth(const double* noise, void* out, int32_t out_dtype, double* tmp, int64_t batch, int32_t H,
-                               int32_t W, double depth_scale, const double* weights, int32_t radius, void* stream) {
-  AWX_REQUIRE(batch >= 0 && H >= 0 && W >= 0, AWX_E_ARG, "awx_synth_depth: negative size");
-  if (batch == 0 || H == 0 || W == 0) return AWX_OK;
-  AWX_REQUIRE(noise && out && tmp && weights, AWX_E_ARG, "awx_synth_depth: NULL pointer");
-  AWX_REQUIRE(radius >= 0 && radius <= 32, AWX_E_UNSUPPORTED, "awx_synth_depth: radius %d outside 0..32", radius);
-  AWX_REQUIRE(out_dtype == AWX_F32 || out_dtype == AWX_F64, AWX_E_ARG, "awx_synth_depth: unknown out dtype");
+namespace awx {
+// scipy.ndimage.gaussian_filter (fp64, mode='reflect') of [B,H,W] planes: vertical pass (adding the ramp
+// (y/H)*ramp_scale on the fly) into tmp, horizontal pass into out, then max(., floor_value).
+int launch_gauss_f64(const double* in, void* out, int32_t out_dtype, double* tmp, int64_t batch, int32_t H, int32_t W,
+                     double ramp_scale, double floor_value, const double* weights, int32_t radius, cudaStream_t s) {
   GaussTaps taps{};
   taps.radius = radius;
   for (int j = 0; j <= radius; ++j) taps.w[j] = weights[radius + j];
@@ -494,15 +492,26 @@ extern "C" int awx_synth_depth(const double* noise, void* out, int32_t out_dtype
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  depth_pass_kernel<true, double><<<(unsigned)blocks, 256, 0, s>>>(noise, tmp, H, W, total, taps, depth_scale);
+  depth_pass_kernel<true, double><<<(unsigned)blocks, 256, 0, s>>>(in, tmp, H, W, total, taps, ramp_scale, floor_value);
   AWX_CUDA(cudaGetLastError());
   note_launch();
   if (out_dtype == AWX_F64)
-    depth_pass_kernel<false, double><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<double*>(out), H, W, total, taps, depth_scale);
+    depth_pass_kernel<false, double><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<double*>(out), H, W, total, taps, ramp_scale, floor_value);
   else
-    depth_pass_kernel<false, float><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<float*>(out), H, W, total, taps, depth_scale);
+    depth_pass_kernel<false, float><<<(unsigned)blocks, 256, 0, s>>>(tmp, static_cast<float*>(out), H, W, total, taps, ramp_scale, floor_value);
   AWX_CUDA(cudaGetLastError());
   note_launch();
   return AWX_OK;
+}
+}  // namespace awx
+
+extern "C" int awx_synth_depth(const double* noise, void* out, int32_t out_dtype, double* tmp, int64_t batch, int32_t H,
+                               int32_t W, double depth_scale, const double* weights, int32_t radius, void* stream) {
+  AWX_REQUIRE(batch >= 0 && H >= 0 && W >= 0, AWX_E_ARG, "awx_synth_depth: negative size");
+  if (batch == 0 || H == 0 || W == 0) return AWX_OK;
+  AWX_REQUIRE(noise && out && tmp && weights, AWX_E_ARG, "awx_synth_depth: NULL pointer");
+  AWX_REQUIRE(radius >= 0 && radius <= 32, AWX_E_UNSUPPORTED, "awx_synth_depth: radius %d outside 0..32", radius);
+  AWX_REQUIRE(out_dtype == AWX_F32 || out_dtype == AWX_F64, AWX_E_ARG, "awx_synth_depth: unknown out dtype");
+  return launch_gauss_f64(noise, out, out_dtype, tmp, batch, H, W, depth_scale, 1.0, weights, radius,
+                          static_cast<cudaStream_t>(stream));
 }

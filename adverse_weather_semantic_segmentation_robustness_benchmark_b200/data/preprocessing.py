@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from .. import _lib, ops
+from .. import _lib, ops, ops_prep
 
 logger = logging.getLogger(__name__)
 
@@ -256,3 +256,46 @@ class WeatherDegradationTransforms:
         """:227-248: draws the N(0,10) field on the host, filters on the device; fp64 [H,W]."""
         noise = np.random.normal(0, 10, (height, width))
         return self.synthetic_depth(noise)[0].cpu().numpy()
+
+    def get_fog_density_map(self, image: np.ndarray, depth: Optional[np.ndarray] = None) -> np.ndarray:
+        """:250-288: fog density in [0,1] for the fog-density-aware loss.  `image`: HWC float in [0,1]
+        (the reference's contract; uint8 frames are taken as they are); `depth`: [H,W] or None (then the
+        synthetic depth is drawn from the global NumPy RNG as the reference does)."""
+        h, w = image.shape[:2]
+        if depth is None:
+            depth = self._generate_synthetic_depth(h, w)
+        img = np.ascontiguousarray(image)
+        if img.dtype not in (np.uint8, np.float32, np.float64):
+            img = img.astype(np.float64)
+        out = ops_prep.fog_density_map(torch.from_numpy(img)[None], torch.from_numpy(np.ascontiguousarray(depth))[None])
+        return out[0].cpu().numpy()
+
+
+class DepthEstimationPreprocessor:
+    """Depth estimation preprocessor (reference: data/preprocessing.py:291-411); the per-pixel work of
+    ``estimate_depth`` runs in libawx.so (awx_estimate_depth)."""
+
+    def __init__(self) -> None:
+        self.depth_model = None
+        logger.info("Initialized DepthEstimationPreprocessor")
+
+    def estimate_depth(self, image: np.ndarray) -> np.ndarray:
+        """:304-326: uint8 RGB HWC -> fp64 [H,W] in [0,1]."""
+        return self._geometric_depth_estimation(image)
+
+    def _geometric_depth_estimation(self, image: np.ndarray) -> np.ndarray:
+        """:328-367: perspective ramp, sky / road bands, Laplacian texture cue, Gaussian sigma=2."""
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise TypeError("libawx estimates depth from uint8 RGB HWC frames; got %s %s" % (image.dtype, image.shape))
+        out = ops_prep.estimate_depth(torch.from_numpy(np.ascontiguousarray(image))[None], scipy_gaussian_weights(2.0))
+        return out[0].cpu().numpy()
+
+    def estimate_depth_batch(self, images) -> torch.Tensor:
+        """Batched, device-resident extension: uint8 [B,H,W,3] -> fp64 [B,H,W] (stays on the GPU)."""
+        img = torch.from_numpy(np.ascontiguousarray(images)) if isinstance(images, np.ndarray) else images
+        return ops_prep.estimate_depth(img, scipy_gaussian_weights(2.0))
+
+    def depth_to_disparity(self, depth: np.ndarray, baseline: float = 0.54) -> np.ndarray:
+        """:369-384 (a handful of host scalars per call in the reference's users; kept as NumPy)."""
+        return baseline / np.maximum(depth, 1e-6)
+

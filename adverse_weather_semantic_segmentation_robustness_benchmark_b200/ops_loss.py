@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import _lib, ops
@@ -101,21 +102,19 @@ def fog_loss_terms(logits, depth_pred, labels, fog_density, depth_tgt, sens: flo
 
 def temperature_grid_search(logits: torch.Tensor, targets: torch.Tensor) -> float:
     """ConfidenceCalibration.optimize_temperature (evaluation/metrics.py:283-321): T in
-    linspace(0.1, 10, 100) minimising the mean NLL over non-ignored pixels; first minimum wins.
-    Each candidate is one awx_fogloss pass over logits/T (materialised by awx_score)."""
-    x = ops.to_device(logits, torch.float32)
-    if x.dim() != 4:
-        raise ValueError("optimize_temperature expects [B,C,H,W] logits")
-    lab = ops.normalise_labels(targets)
-    if bool((lab == 255).any()):
-        raise NotImplementedError("optimize_temperature with ignored (255) pixels is not wired to the kernel yet")
+    linspace(0.1, 10, 100) minimising the mean NLL over non-ignored rows; first minimum wins.
+    One awx_temperature_nll pass over the logits evaluates the whole grid.  Rows are
+    ``logits.view(-1, C)`` exactly as the reference flattens them (for an NCHW tensor that is not a
+    pixel's class vector; pass [N, C] logits for the per-pixel meaning)."""
+    from . import ops_prep
+    temps = torch.linspace(0.1, 10.0, 100)
+    sums, n_valid, n_bad = ops_prep.temperature_nll(logits, targets, temps)
+    if n_bad:
+        raise IndexError("Target out of bounds (labels outside [0, C) other than the ignored 255)")
     best_t, best_nll = 1.0, float("inf")
-    n = float(x.shape[0] * x.shape[2] * x.shape[3])
-    for temp in torch.linspace(0.1, 10.0, 100):
-        scaled = ops.score(x, temperature=float(temp), want_fused=True)["fused"]
-        sums, _, _, _, _ = fogloss_raw(scaled, lab, None, None, None, 0.0, False, False)
-        nll = float(sums[0].item() / n)
-        nll = float(torch.tensor(nll, dtype=torch.float32))
+    for temp, total in zip(temps, sums):
+        # F.cross_entropy returns the fp32 mean; no valid rows -> nan, which never compares smaller
+        nll = float(np.float32(total / n_valid)) if n_valid else float("nan")
         if nll < best_nll:
             best_nll, best_t = nll, temp.item()
     return best_t

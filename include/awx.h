@@ -151,7 +151,7 @@ int awx_member_variance(const float* logits_a, const float* logits_b, float* out
  * ---------------------------------------------------------------------------------- */
 
 enum { AWX_CLEAN = 0, AWX_FOG = 1, AWX_RAIN = 2, AWX_SNOW = 3, AWX_NIGHT = 4 };
-enum { AWX_F32 = 0, AWX_F64 = 1 };
+enum { AWX_F32 = 0, AWX_F64 = 1, AWX_BF16 = 2, AWX_U8 = 3 };
 
 /* One per image (HOST array; awx_corrupt copies it into the head of its workspace).
  * Field/overlay offsets are in ELEMENTS of the arrays passed to awx_corrupt. */
@@ -210,6 +210,54 @@ int awx_fogloss(const float* logits, const void* labels, int32_t label_dtype,
 
 /* x[i] *= *scale (device scalar) -- backward of a mean-reduced loss with grad_output != 1. */
 int awx_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Callers and producers either side of the hot path.
+ * ---------------------------------------------------------------------------------- */
+
+/* albumentations Normalize(mean, std, max_pixel_value=255) + ToTensorV2 (data/loader.py:196-199):
+ * uint8 [B,H,W,3] -> fp32 (AWX_F32) or bf16 (AWX_BF16) [B,3,H,W];
+ * out = (x - mean255[c]) * rdenom[c] as two separately rounded fp32 operations.
+ * mean255 / rdenom: HOST float[3] (mean*255 and 1/(std*255), formed by the caller in fp32). */
+int awx_normalize_chw(const uint8_t* img, void* out, int32_t out_dtype, int64_t batch, int32_t height, int32_t width,
+                      const float* mean255 /*HOST*/, const float* rdenom /*HOST*/, void* stream);
+
+/* WeatherAugmentationPipeline._apply_style_transfer (data/loader.py:364-385):
+ * out = cv2.convertScaleAbs(img, alpha, beta); if has_gain: out[...,2] = trunc(clip(out[...,2] * blue_gain, 0, 255)).
+ * img / out: uint8, n_pixels * 3 bytes (HWC). */
+int awx_style_transfer(const uint8_t* img, uint8_t* out, int64_t n_pixels, float alpha, float beta, double blue_gain,
+                       int32_t has_gain, void* stream);
+
+/* ConfidenceCalibration.optimize_temperature (evaluation/metrics.py:283-321), the whole grid in one pass:
+ * sums[t] += sum over valid rows of cross_entropy(row / temperatures[t], label); sums[n] += valid rows;
+ * sums[n+1] += labels outside [0,C) (torch raises on those).  rows are C consecutive floats of `logits`
+ * (the reference's logits.view(-1, C)); labels: one per row; temperatures: HOST float[n_temps], all > 0.
+ * sums: device fp64 [n_temps + 2], accumulates (zero it first).  workspace: awx_temperature_workspace_bytes(). */
+size_t awx_temperature_workspace_bytes(int32_t n_temps);
+int awx_temperature_nll(const float* logits, const void* labels, int32_t label_dtype, int64_t rows, int32_t num_classes,
+                        int32_t ignore_index, const float* temperatures /*HOST*/, int32_t n_temps, double* sums,
+                        void* workspace, void* stream);
+
+/* WeatherDegradationTransforms.get_fog_density_map (data/preprocessing.py:250-288) in two calls around the
+ * host's percentile lerp:
+ *   awx_local_contrast: img [B,H,W,3] (AWX_U8, or AWX_F32 / AWX_F64 in [0,1], converted as (img*255).astype(uint8))
+ *       -> contrast fp32 [B,H,W] = sqrt(box5((gray - box5(gray))^2)), plus, per image, the order statistics of
+ *       ranks rank_lo and rank_hi (0-based, ascending) of its contrast values: order_stats fp32 [B,2].
+ *   awx_fog_density_finish: out = clip((1 - contrast / denom[b]) * (0.3 + 0.7 * depth / max(depth_b)), 0, 1);
+ *       denom: device fp32 [B] = max_contrast + 1e-8; depth / out: fp64 or fp32 [B,HW].
+ * workspace: awx_fog_density_workspace_bytes(batch) bytes, the same buffer for both calls. */
+size_t awx_fog_density_workspace_bytes(int64_t batch);
+int awx_local_contrast(const void* img, int32_t img_dtype, float* contrast, int64_t batch, int32_t height, int32_t width,
+                       int64_t rank_lo, int64_t rank_hi, float* order_stats, void* workspace, void* stream);
+int awx_fog_density_finish(const float* contrast, const void* depth, int32_t depth_dtype, const float* denom, void* out,
+                           int64_t batch, int64_t pixels_per_image, void* workspace, void* stream);
+
+/* DepthEstimationPreprocessor._geometric_depth_estimation (data/preprocessing.py:332-367):
+ * img uint8 [B,H,W,3] -> out fp64 [B,H,W]: perspective ramp with sky / road bands, minus 0.3 * |Laplacian(gray)| /
+ * (max + 1e-8), clipped to [0,1], then scipy's gaussian_filter(sigma=2) (weights: HOST fp64 [2*radius+1]).
+ * tmp: fp64 [B,H,W]; amax_workspace: int32 [B]. */
+int awx_estimate_depth(const uint8_t* img, double* out, double* tmp, int64_t batch, int32_t height, int32_t width,
+                       const double* weights /*HOST*/, int32_t radius, int32_t* amax_workspace, void* stream);
 
 #ifdef __cplusplus
 }

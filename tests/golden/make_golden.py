@@ -179,6 +179,60 @@ def loss_cases():
     np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
 
 
+def prep_cases():
+    """fog-density map, depth estimation, style transfer, temperature grid."""
+    pre = refshim.preprocessing()
+    met = refshim.metrics()
+    ldr = refshim.loader()
+    out = {"versions": versions()}
+    # W multiples of 16: no scalar tail in OpenCV's filter2D vector body (see csrc/scene.cu header)
+    for tag, (h, w) in {"a": (64, 96), "b": (50, 70), "c": (33, 48)}.items():
+        np.random.seed(21)
+        image = np.random.randint(0, 255, (h, w, 3), dtype=np.uint8)
+        out[f"{tag}_image"] = image
+        t = pre.WeatherDegradationTransforms(seed=13)
+        depth = t._generate_synthetic_depth(h, w)
+        out[f"{tag}_depth"] = depth
+        imgf = image.astype(np.float32) / 255.0
+        out[f"{tag}_fogmap"] = t.get_fog_density_map(imgf, depth)
+        t2 = pre.WeatherDegradationTransforms(seed=14)
+        out[f"{tag}_fogmap_seed14"] = t2.get_fog_density_map(imgf)  # depth drawn from the global RNG
+        out[f"{tag}_est_depth"] = pre.DepthEstimationPreprocessor().estimate_depth(image)
+    # style transfer: every byte value in every channel, plus a random frame
+    ramp = np.repeat(np.arange(256, dtype=np.uint8).reshape(16, 16, 1), 3, axis=2)
+    np.random.seed(5)
+    rnd = np.random.randint(0, 256, (40, 56, 3), dtype=np.uint8)
+    out["style_ramp"], out["style_rnd"] = ramp, rnd
+    pipe = ldr.WeatherAugmentationPipeline()
+    for kind in ("fog", "rain", "snow", "night", "clean"):
+        out[f"style_ramp_{kind}"] = pipe._apply_style_transfer(ramp.copy(), kind)
+        out[f"style_rnd_{kind}"] = pipe._apply_style_transfer(rnd.copy(), kind)
+    # full pipeline with the reference's RNG order (weather choice, corruption draws, style coin)
+    np.random.seed(77)
+    frame = np.random.randint(0, 255, (48, 64, 3), dtype=np.uint8)
+    out["aug_frame"] = frame
+    for seed in (1, 2, 3, 4):
+        np.random.seed(seed)
+        p2 = ldr.WeatherAugmentationPipeline(style_transfer_prob=0.6)
+        np.random.seed(seed)
+        out[f"aug_seed{seed}"] = p2.apply_domain_adaptation_augmentation(frame.copy())
+    # temperature grid search
+    torch.manual_seed(31)
+    cal = met.ConfidenceCalibration()
+    for tag, (b, c, h, w, scale, ign) in {"t19": (2, 19, 16, 24, 3.0, 0.05), "t5": (1, 5, 12, 20, 0.5, 0.0)}.items():
+        logits = torch.randn(b, c, h, w) * scale
+        targets = torch.randint(0, c, (b, h, w))
+        if ign > 0:
+            targets[torch.rand(b, h, w) < ign] = 255
+        out[f"{tag}_logits"], out[f"{tag}_targets"] = logits.numpy(), targets.numpy()
+        out[f"{tag}_best_t"] = np.float64(cal.optimize_temperature(logits, targets))
+        rows = logits.view(-1, c)[targets.view(-1) != 255]
+        tg = targets.view(-1)[targets.view(-1) != 255]
+        out[f"{tag}_nll"] = np.array([torch.nn.functional.cross_entropy(rows / t, tg).item()
+                                      for t in torch.linspace(0.1, 10.0, 100)], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "prep.npz"), **out)
+
+
 if __name__ == "__main__":
     if not refshim.available():
         raise SystemExit("reference not present; golden files can only be regenerated in the build container")
@@ -186,6 +240,7 @@ if __name__ == "__main__":
     metric_cases()
     fusion_cases()
     loss_cases()
+    prep_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

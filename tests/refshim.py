@@ -54,6 +54,26 @@ def model():
     return _cache["mod"]
 
 
+def loader():
+    """data/loader.py imported through the reference package with albumentations stubbed (not installed
+    here; only its names are needed at import time -- SURVEY.md Appendix A.2)."""
+    if "loader" not in _cache:
+        if "albumentations" not in sys.modules:
+            alb = types.ModuleType("albumentations")
+            for name in ("Compose", "HorizontalFlip", "RandomBrightnessContrast", "Normalize"):
+                setattr(alb, name, type(name, (), {"__init__": lambda self, *a, **k: None}))
+            albp = types.ModuleType("albumentations.pytorch")
+            albp.ToTensorV2 = type("ToTensorV2", (), {"__init__": lambda self, *a, **k: None})
+            alb.pytorch = albp
+            sys.modules["albumentations"] = alb
+            sys.modules["albumentations.pytorch"] = albp
+        if _SRC not in sys.path:
+            sys.path.insert(0, _SRC)
+        import importlib
+        _cache["loader"] = importlib.import_module(PKG + ".data.loader")
+    return _cache["loader"]
+
+
 def ensemble_with_fixed_members(l1, l2, strategy="weighted_average", temperature_scaling=True,
                                 raw_weights=None, temperature=None, d1=None, d2=None):
     """The reference's EnsembleModel with two tiny producers injected, so that its own

@@ -208,3 +208,61 @@ def test_fog_density_from_depth(golden):
     g = golden("loss")
     d = torch.from_numpy(g["depth"]).squeeze(1)
     _eq(ol.fog_density_from_depth(d).numpy(), g["fd_from_depth"], _same_versions(g), rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------- producers / consumers either side (8f rows 2-4)
+from oracle import prep as op  # noqa: E402
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_fog_density_map_matches_reference(golden, tag):
+    g = golden("prep")
+    exact = _same_versions(g)
+    img = g[f"{tag}_image"].astype(np.float32) / 255.0
+    _eq(op.fog_density_map(img, g[f"{tag}_depth"]), g[f"{tag}_fogmap"], exact, atol=1e-6, rtol=1e-5)
+    # depth=None path: the synthetic depth comes from the global RNG exactly as in the reference
+    np.random.seed(14)
+    depth = ow.depth_from_noise(np.random.normal(0, 10, img.shape[:2]))
+    _eq(op.fog_density_map(img, depth), g[f"{tag}_fogmap_seed14"], exact, atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_estimate_depth_matches_reference(golden, tag):
+    g = golden("prep")
+    _eq(op.estimate_depth(g[f"{tag}_image"]), g[f"{tag}_est_depth"], _same_versions(g), atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["fog", "rain", "snow", "night", "clean"])
+def test_style_transfer_matches_reference(golden, kind):
+    g = golden("prep")
+    for src in ("ramp", "rnd"):
+        got = op.style_transfer(g[f"style_{src}"].copy(), kind)
+        assert got.dtype == np.uint8
+        assert np.array_equal(got, g[f"style_{src}_{kind}"])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_domain_adaptation_augmentation_matches_reference(golden, seed):
+    g = golden("prep")
+    np.random.seed(seed)
+    got = op.domain_adaptation_augmentation(g["aug_frame"].copy(), style_transfer_prob=0.6)
+    d = np.abs(got.astype(int) - g[f"aug_seed{seed}"].astype(int))
+    assert d.max() <= (0 if _same_versions(g) else 1)
+
+
+@pytest.mark.parametrize("tag", ["t19", "t5"])
+def test_temperature_grid_matches_reference(golden, tag):
+    g = golden("prep")
+    logits, targets = torch.from_numpy(g[f"{tag}_logits"]), torch.from_numpy(g[f"{tag}_targets"])
+    _eq(op.temperature_nll(logits, targets).double().numpy(), g[f"{tag}_nll"], _same_versions(g), rtol=1e-6)
+    assert op.optimize_temperature(logits, targets) == float(g[f"{tag}_best_t"])
+
+
+def test_normalize_chw_restatement():
+    """Parity unpinned (albumentations absent): the restatement against first principles in fp64."""
+    rng = np.random.RandomState(3)
+    img = rng.randint(0, 256, (20, 28, 3)).astype(np.uint8)
+    got = op.normalize_chw(img)
+    assert got.dtype == np.float32 and got.shape == (3, 20, 28)
+    want = (img.astype(np.float64) / 255.0 - np.array(op.IMAGENET_MEAN)) / np.array(op.IMAGENET_STD)
+    np.testing.assert_allclose(got, want.transpose(2, 0, 1), rtol=0, atol=2e-6)
