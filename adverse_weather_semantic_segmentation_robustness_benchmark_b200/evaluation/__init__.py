@@ -7,7 +7,11 @@ from .metrics import (
     RobustnessMetrics,
 )
 
+from .streaming import StreamingEvaluator, evaluate_model
+
 __all__ = [
+    "StreamingEvaluator",
+    "evaluate_model",
     "IoUMetrics",
     "ConfidenceCalibration",
     "EnsembleDisagreementMetrics",

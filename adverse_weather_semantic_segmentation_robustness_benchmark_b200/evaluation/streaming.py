@@ -89,7 +89,8 @@ class StreamingEvaluator:
 
     def per_condition(self) -> Dict[str, Dict[str, float]]:
         host = self.bins.cpu().numpy()
-        return {c: self._metrics_of(host[i]) for i, c in enumerate(self.conditions) if host[i].any()}
+        return {c: self._metrics_of(host[i]) for i, c in enumerate(self.conditions)
+                if host[i].any() and not c.startswith("__")}
 
     def finalize(self) -> Dict[str, float]:
         """The reference's ``evaluate_model`` result dict (evaluate.py:214-272) from the merged bins."""
@@ -98,7 +99,7 @@ class StreamingEvaluator:
         res: Dict[str, float] = {"overall_miou": total["mean_iou"]}
         mious = {}
         for i, c in enumerate(self.conditions):
-            if not host[i].any():
+            if not host[i].any() or c.startswith("__"):  # "__other__": frames counted in the overall numbers only
                 continue
             m = self._metrics_of(host[i])
             mious[c] = m["mean_iou"]
@@ -116,3 +117,62 @@ class StreamingEvaluator:
             if degr:
                 res["robustness_degradation_ratio"] = np.mean(degr)
         return res
+
+
+OTHER = "__other__"
+
+
+def evaluate_model(model, test_loader, metrics=None, device=None, config=None, group=None) -> Dict[str, float]:
+    """Drop-in for the reference's ``evaluate_model(model, test_loader, metrics, device, config)``
+    (scripts/evaluate.py:134-274; trainer twin training/trainer.py:377-478), streaming and sharded.
+
+    Same loop -- ``outputs = model(images)`` per batch, frames grouped by ``batch['weather_condition']`` --
+    but nothing is concatenated: every run of consecutive frames with the same condition is scored by one
+    ``awx_score`` launch into that condition's integer bins.  An ensemble model (outputs carry
+    ``segformer_seg`` and ``deeplabv3plus_seg``) is fused inside the kernel with the model's own
+    ``ensemble_strategy`` / ``ensemble_weights`` / ``temperature``; any other model is scored on
+    ``outputs['segmentation']``.  Under ``torch.distributed`` every rank evaluates its shard of the loader
+    and one ``all_reduce`` merges the bins.  ``metrics`` / ``device`` are accepted for signature
+    compatibility (``metrics.num_classes`` and ``metrics.weather_conditions`` are honoured)."""
+    get = (lambda k, d: config.get(k, d)) if config is not None and hasattr(config, "get") else (lambda k, d: d)
+    conditions = list(get("data.weather_conditions", None) or getattr(metrics, "weather_conditions", None)
+                      or DEFAULT_CONDITIONS)
+    num_classes = int(getattr(metrics, "num_classes", None) or get("model.num_classes", 19))
+    ev = None
+    was_training = getattr(model, "training", False)
+    if hasattr(model, "eval"):
+        model.eval()
+    with torch.no_grad():
+        for batch in test_loader:
+            images = batch["image"].to(device) if device is not None else batch["image"]
+            labels = batch["label"].to(device) if device is not None else batch["label"]
+            weather = list(batch.get("weather_condition", ["clean"] * images.size(0)))
+            outputs = model(images)
+            ensemble = "segformer_seg" in outputs and "deeplabv3plus_seg" in outputs
+            if ev is None:
+                if ensemble:
+                    ts = bool(getattr(model, "temperature_scaling", False))
+                    raw_w = getattr(model, "ensemble_weights", torch.ones(2) / 2).detach().float().cpu()
+                    temp = float(model.temperature.detach().float().cpu()[0]) if ts else None
+                    ev = StreamingEvaluator(num_classes, conditions + [OTHER], strategy=getattr(model, "ensemble_strategy", "mean"),
+                                            ensemble_weights=raw_w.tolist(), temperature=temp, ensemble=True)
+                else:
+                    ev = StreamingEvaluator(num_classes, conditions + [OTHER], ensemble=False, temperature=None)
+            la = outputs["segformer_seg"] if ensemble else outputs["segmentation"]
+            lb = outputs["deeplabv3plus_seg"] if ensemble else None
+            # runs of consecutive frames with the same condition are contiguous views: no copies
+            i = 0
+            while i < len(weather):
+                j = i
+                while j + 1 < len(weather) and weather[j + 1] == weather[i]:
+                    j += 1
+                cond = weather[i] if weather[i] in conditions else OTHER
+                ev.update(cond, la[i:j + 1], None if lb is None else lb[i:j + 1], labels[i:j + 1])
+                i = j + 1
+    if was_training and hasattr(model, "train"):
+        model.train()
+    if ev is None:
+        return {}
+    ev.all_reduce(group)
+    return ev.finalize()
+

@@ -1,0 +1,123 @@
+"""evaluate_model drop-in (scripts/evaluate.py:134-274) on the GPU against the oracle's restatement of
+the reference's end-of-loop metric calls on the concatenated tensors."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om, fusion as of_
+
+pytestmark = pytest.mark.gpu
+
+C, H, W = 19, 48, 64
+CONDS = ["clean", "fog", "rain", "snow", "night"]
+
+
+class _Config:
+    def __init__(self, d):
+        self.d = d
+
+    def get(self, k, default=None):
+        return self.d.get(k, default)
+
+
+def _loader(seed, n_batches=4, bsz=3, with_other=True):
+    gen = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    names = CONDS + (["hail"] if with_other else [])
+    out = []
+    for _ in range(n_batches):
+        out.append({
+            "image": torch.rand(bsz, 3, H, W, generator=gen),
+            "label": torch.randint(0, C, (bsz, H, W), generator=gen),
+            "weather_condition": [names[i] for i in rng.randint(0, len(names), bsz)],
+            "_la": torch.randn(bsz, C, H, W, generator=gen) * 2,
+            "_lb": torch.randn(bsz, C, H, W, generator=gen) * 2,
+        })
+    out[0]["weather_condition"][0] = "clean"   # the degradation ratios need a clean frame
+    out[0]["label"][0, :3] = 255
+    return out
+
+
+class _Ensemble(torch.nn.Module):
+    """Stands in for EnsembleModel: returns the member logits stashed in the batch."""
+
+    def __init__(self, batches, strategy="weighted_average", ts=True):
+        super().__init__()
+        self.batches, self.i = batches, 0
+        self.ensemble_strategy, self.temperature_scaling = strategy, ts
+        self.ensemble_weights = torch.nn.Parameter(torch.tensor([0.3, 0.9]))
+        self.temperature = torch.nn.Parameter(torch.tensor([1.7]))
+
+    def forward(self, x):
+        b = self.batches[self.i]
+        self.i += 1
+        la, lb = b["_la"].cuda(), b["_lb"].cuda()
+        return {"segmentation": None, "segformer_seg": la, "deeplabv3plus_seg": lb}
+
+
+class _Single(torch.nn.Module):
+    def __init__(self, batches):
+        super().__init__()
+        self.batches, self.i = batches, 0
+
+    def forward(self, x):
+        b = self.batches[self.i]
+        self.i += 1
+        return {"segmentation": b["_la"].cuda()}
+
+
+def _expected(batches, fuse):
+    logits = torch.cat([fuse(b["_la"], b["_lb"]) for b in batches])
+    tg = torch.cat([b["label"] for b in batches])
+    weather = sum((b["weather_condition"] for b in batches), [])
+    res = {"overall_miou": om.iou(logits, tg, C)["mean_iou"], "expected_calibration_error": om.ece(logits, tg)["ece"]}
+    mious = {}
+    for c in CONDS:
+        idx = [i for i, wname in enumerate(weather) if wname == c]
+        if idx:
+            mious[c] = om.iou(logits[idx], tg[idx], C)["mean_iou"]
+            res[f"miou_{c}"] = mious[c]
+            res[f"ece_{c}"] = om.ece(logits[idx], tg[idx])["ece"]
+    degr = []
+    for c in CONDS[1:]:
+        if c in mious and "clean" in mious:
+            res[f"robustness_degradation_{c}"] = om.degradation_ratio(mious["clean"], mious[c])
+            degr.append(res[f"robustness_degradation_{c}"])
+    if degr:
+        res["robustness_degradation_ratio"] = np.mean(degr)
+    return res
+
+
+def _check(res, want):
+    for k, v in want.items():
+        assert k in res, k
+        if k.startswith("ece") or k == "expected_calibration_error":
+            np.testing.assert_allclose(res[k], v, rtol=1e-5, atol=1e-8, err_msg=k)
+        else:
+            assert res[k] == v, (k, res[k], v)
+
+
+@pytest.mark.parametrize("strategy,ts", [("weighted_average", True), ("mean", False), ("max_confidence", True)])
+def test_evaluate_model_ensemble(strategy, ts):
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import evaluate_model
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import RobustnessMetrics
+    batches = _loader(3)
+    model = _Ensemble(batches, strategy, ts)
+    cfg = _Config({"data.weather_conditions": CONDS})
+    res = evaluate_model(model, batches, RobustnessMetrics(C), torch.device("cuda"), cfg)
+    raw_w, temp = torch.tensor([0.3, 0.9]), torch.tensor([1.7])
+    want = _expected(batches, lambda a, b: of_.fuse_logits(a, b, strategy, raw_w, temp if ts else None))
+    _check(res, want)
+    tg = torch.cat([b["label"] for b in batches])
+    exact = om.disagreement_auroc([torch.cat([b["_la"] for b in batches]), torch.cat([b["_lb"] for b in batches])], tg)
+    assert abs(res["ensemble_disagreement_auroc"] - exact) <= 2e-3
+    assert not any(k.startswith("miou___") or "hail" in k for k in res)
+
+
+def test_evaluate_model_single_member():
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import evaluate_model
+    batches = _loader(5, with_other=False)
+    res = evaluate_model(_Single(batches), batches, None, torch.device("cuda"), _Config({"data.weather_conditions": CONDS}))
+    _check(res, _expected(batches, lambda a, b: a))
+    assert "ensemble_disagreement_auroc" not in res

@@ -194,3 +194,23 @@ def test_robustness_summary_matches_reference(golden):
     got = [rob.compute_robustness_degradation_ratio(a, b) for a, b in ((0.5, 0.4), (0.0, 0.3), (0.4, 0.5), (0.78, 0.65))]
     assert np.array_equal(np.array(got), g["degr"])
     assert rob.weather_conditions == ["clean", "fog", "rain", "snow", "night"]
+
+
+def test_percentile_scalars_match_numpy():
+    """The host part of get_fog_density_map's 95th percentile: NumPy's index / gamma / lerp scalars."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops_prep
+    rng = np.random.RandomState(0)
+    for n in (3, 5, 17, 1000, 6144, 50 * 70, 1024 * 2048):
+        a = rng.rand(n).astype(np.float32)
+        lo, hi, gamma = ops_prep.percentile_indices(n, 95, np.float32)
+        srt = np.sort(a)
+        got = ops_prep.lerp(srt[lo], srt[hi], gamma)
+        assert got.dtype == np.float32 and got == np.percentile(a, 95), n
+
+
+def test_normalize_params_are_fp32_albumentations_scalars():
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops_prep
+    m, r = ops_prep.normalize_params(ops_prep.IMAGENET_MEAN, ops_prep.IMAGENET_STD)
+    assert m.dtype == np.float32 and r.dtype == np.float32
+    assert np.array_equal(m, np.array(ops_prep.IMAGENET_MEAN, np.float32) * np.float32(255.0))
+    assert np.array_equal(r, np.float32(1) / (np.array(ops_prep.IMAGENET_STD, np.float32) * np.float32(255.0)))
