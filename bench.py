@@ -383,6 +383,19 @@ def run_e2e(args, wl, device, world, barrier, max_over_ranks, px_step):
         host.copy_(t)
         return host
 
+    # every rank stages its whole step's inputs in host memory (25 GB at the default size): refuse
+    # rather than push the box into swap / the OOM killer when the ranks together would not fit
+    need = sum(t.numel() * t.element_size() for t in (wl.images, wl.labels, wl.la, wl.lb))
+    need += sum(v.numel() * v.element_size() for v in wl.fields.values() if v is not None)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = None
+    if avail is not None and need * world * 1.25 > avail:
+        return {"value": None, "unit": "Mpixel/s", "skipped": "host staging buffers (%.1f GB x %d ranks) exceed the "
+                "available host memory (%.1f GB)" % (need / 1e9, world, avail / 1e9)}
+
     try:
         h_images, h_labels = pin(wl.images), pin(wl.labels)
         h_la, h_lb = pin(wl.la), pin(wl.lb)
