@@ -54,3 +54,17 @@ extern "C" int awx_device_info(int* sms, int* major, int* minor) {
   if (minor) *minor = prop.minor;
   return AWX_OK;
 }
+
+/* One call per condition: the corruption kernels of a batch and the fused scoring pass of the logits the
+ * caller's model produced, enqueued back to back on `stream` (SURVEY.md 8b "awx_corrupt_score").  The two stages
+ * share no per-pixel data (the corrupted frames feed the backbone, the score reads its logits), so a single
+ * kernel would only interleave two independent streams; see DESIGN.md section 4. */
+extern "C" int awx_corrupt_score(const uint8_t* img, uint8_t* out, int32_t H, int32_t W, const AwxCorruptParams* params,
+                                 const void* field, int32_t field_dtype, const int32_t* items, int64_t n_items,
+                                 void* workspace, const float* logits_a, const float* logits_b, const void* labels,
+                                 int64_t batch, const AwxScoreConfig* cfg, int64_t* bins, const AwxScoreMaps* maps,
+                                 void* stream) {
+  int rc = awx_corrupt(img, out, batch, H, W, params, field, field_dtype, items, n_items, workspace, stream);
+  if (rc != AWX_OK) return rc;
+  return awx_score(logits_a, logits_b, labels, batch, (int64_t)H * W, cfg, bins, maps, stream);
+}

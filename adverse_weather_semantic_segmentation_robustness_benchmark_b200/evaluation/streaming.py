@@ -47,6 +47,7 @@ class StreamingEvaluator:
         # always needs the CUDA device)
         dev = ops.require_cuda() if bins_device is None else torch.device(bins_device)
         self.bins = torch.zeros((len(self.conditions), self.words), dtype=torch.int64, device=dev)
+        self._cfg_cache = {}
 
     def reset(self) -> None:
         self.bins.zero_()
@@ -58,6 +59,22 @@ class StreamingEvaluator:
         ops.score(logits_a, logits_b if self.ensemble else None, labels, strategy=self.strategy,
                   w0=self.w0, w1=self.w1, temperature=self.temperature, ignore_index=self.ignore_index,
                   ece_bins=self.ece_bins, auroc_bins=self.auroc_bins, bins=row)
+
+    def update_corrupted(self, condition: str, images: torch.Tensor, params, field, items, out: torch.Tensor,
+                         workspace: torch.Tensor, logits_a: torch.Tensor, logits_b: Optional[torch.Tensor],
+                         labels: torch.Tensor) -> None:
+        """One awx_corrupt_score call: corrupt `images` (uint8 [B,H,W,3], device) into `out` for the model's
+        next batch and score this batch's logits into the condition's bins.  Inputs must already be
+        contiguous device tensors (labels uint8 or int64)."""
+        row = self.bins[self.conditions.index(condition)]
+        key = (logits_a.shape[1], labels.dtype)
+        cfg = self._cfg_cache.get(key)
+        if cfg is None:
+            cfg = ops.score_config(logits_a.shape[1], self.strategy, self.w0, self.w1, self.temperature,
+                                   ops.label_code(labels), self.ignore_index, self.ece_bins, self.auroc_bins)
+            self._cfg_cache[key] = cfg
+        ops.corrupt_score(images, params, field, items, out, workspace, logits_a,
+                          logits_b if self.ensemble else None, labels, cfg, row)
 
     def all_reduce(self, group=None) -> None:
         """Merge the bins of all ranks (NCCL over NVLink on GPUs; any backend that sums int64)."""

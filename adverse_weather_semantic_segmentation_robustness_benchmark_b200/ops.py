@@ -120,6 +120,22 @@ def new_bins(num_classes: int, ece_bins: int = 15, auroc_bins: int = 0) -> torch
     return torch.zeros(lay.total_words, dtype=torch.int64, device=require_cuda())
 
 
+def score_config(num_classes: int, strategy: int, w0: float, w1: float, temperature: Optional[float], label_dtype: int,
+                 ignore_index: int = 255, ece_bins: int = 15, auroc_bins: int = 0, auroc_hi: float = LN2):
+    """AwxScoreConfig (host struct) with the reference's torch.linspace ECE edges."""
+    cfg = _lib.ScoreConfig()
+    cfg.num_classes, cfg.strategy = num_classes, strategy
+    cfg.w0, cfg.w1 = float(w0), float(w1)
+    cfg.use_temperature = 0 if temperature is None else 1
+    cfg.temperature = 1.0 if temperature is None else float(temperature)
+    cfg.label_dtype = label_dtype
+    cfg.ignore_index = ignore_index
+    cfg.ece_bins, cfg.auroc_bins, cfg.auroc_hi = ece_bins, auroc_bins, float(auroc_hi)
+    for i, e in enumerate(ece_edges(ece_bins).numpy()):
+        cfg.ece_edges[i] = float(e)
+    return cfg
+
+
 def score(logits_a: torch.Tensor, logits_b: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, *,
           strategy: int = _lib.FUSE_SINGLE, w0: float = 0.5, w1: float = 0.5,
           temperature: Optional[float] = None, ignore_index: int = 255,
@@ -148,17 +164,8 @@ def score(logits_a: torch.Tensor, logits_b: Optional[torch.Tensor] = None, label
         if lab.numel() != bsz * h * w:
             raise ValueError(f"labels have {lab.numel()} elements, expected {bsz * h * w}")
     nb_auroc = auroc_bins if ens else 0
-    cfg = _lib.ScoreConfig()
-    cfg.num_classes, cfg.strategy = ncls, strategy
-    cfg.w0, cfg.w1 = float(w0), float(w1)
-    cfg.use_temperature = 0 if temperature is None else 1
-    cfg.temperature = 1.0 if temperature is None else float(temperature)
-    cfg.label_dtype = _lib.LABEL_I64 if lab is None else label_code(lab)
-    cfg.ignore_index = ignore_index
-    cfg.ece_bins, cfg.auroc_bins, cfg.auroc_hi = ece_bins, nb_auroc, float(auroc_hi)
-    edges = ece_edges(ece_bins).numpy()
-    for i, e in enumerate(edges):
-        cfg.ece_edges[i] = float(e)
+    cfg = score_config(ncls, strategy, w0, w1, temperature, _lib.LABEL_I64 if lab is None else label_code(lab),
+                       ignore_index, ece_bins, nb_auroc, auroc_hi)
     dev = a.device
     out = {}
     if lab is not None:
@@ -267,3 +274,19 @@ def corrupt(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tens
                          _ptr(items), n_items, _ptr(workspace), _stream())
     _lib.check(rc, "awx_corrupt")
     return out
+
+
+def corrupt_score(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tensor], items: Optional[torch.Tensor],
+                  out: torch.Tensor, workspace: torch.Tensor, logits_a: torch.Tensor, logits_b: Optional[torch.Tensor],
+                  labels: torch.Tensor, cfg, bins: torch.Tensor) -> None:
+    """awx_corrupt_score: one C call per condition -- corrupt `images` into `out` and score the logits into
+    `bins`.  Everything device resident, contiguous and pre-validated (this is the sweep driver's inner call);
+    `cfg` comes from score_config()."""
+    lib = _lib.load()
+    b, h, w, _ = images.shape
+    fdt = _lib.F32 if (field is not None and field.dtype == torch.float32) else _lib.F64
+    rc = lib.awx_corrupt_score(_ptr(images), _ptr(out), h, w, params.ctypes.data_as(C.c_void_p), _ptr(field), fdt,
+                               _ptr(items), 0 if items is None else items.shape[0], _ptr(workspace),
+                               _ptr(logits_a), _ptr(logits_b), _ptr(labels), b, C.byref(cfg), _ptr(bins), None, _stream())
+    _lib.check(rc, "awx_corrupt_score")
+

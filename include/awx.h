@@ -181,6 +181,15 @@ int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int32_t height,
                 const AwxCorruptParams* params /*HOST*/, const void* field, int32_t field_dtype,
                 const int32_t* items, int64_t n_items, void* workspace, void* stream);
 
+/* awx_corrupt followed by awx_score of the same batch (pixels_per_image = height * width) on one stream:
+ * one call per weather condition of the evaluation sweep (scripts/evaluate.py:177-212 per batch). */
+int awx_corrupt_score(const uint8_t* img, uint8_t* out, int32_t height, int32_t width,
+                      const AwxCorruptParams* params /*HOST*/, const void* field, int32_t field_dtype,
+                      const int32_t* items, int64_t n_items, void* workspace,
+                      const float* logits_a, const float* logits_b, const void* labels, int64_t batch,
+                      const AwxScoreConfig* cfg /*HOST*/, int64_t* bins, const AwxScoreMaps* maps /*HOST, may be NULL*/,
+                      void* stream);
+
 /* depth = max(gaussian_filter(ramp + noise, sigma, mode=reflect), 1) in fp64, axis 0 then axis 1,
  * with scipy's symmetric accumulation order (_generate_synthetic_depth, preprocessing.py:235-246).
  * noise: fp64 [B,H,W] drawn by the host; out: fp64 or fp32 [B,H,W]; tmp: fp64 [B,H,W] workspace;

@@ -121,3 +121,32 @@ def test_evaluate_model_single_member():
     res = evaluate_model(_Single(batches), batches, None, torch.device("cuda"), _Config({"data.weather_conditions": CONDS}))
     _check(res, _expected(batches, lambda a, b: a))
     assert "ensemble_disagreement_auroc" not in res
+
+
+def test_corrupt_score_single_call_equals_two_calls():
+    """awx_corrupt_score (one C call per condition) == awx_corrupt followed by awx_score."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.data.preprocessing import (
+        WeatherDegradationTransforms)
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import StreamingEvaluator
+    h, w, b = 64, 96, 3
+    gen = torch.Generator().manual_seed(2)
+    imgs = torch.randint(0, 255, (b, h, w, 3), generator=gen, dtype=torch.uint8).cuda()
+    la = (torch.randn(b, C, h, w, generator=gen) * 2).cuda()
+    lb = (torch.randn(b, C, h, w, generator=gen) * 2).cuda()
+    lab = torch.randint(0, C, (b, h, w), generator=gen).to(torch.uint8).cuda()
+    t = WeatherDegradationTransforms(seed=4)
+    for kind in ("rain", "night"):
+        draws = [t.draw(kind, h, w) for _ in range(b)]
+        prm, fld, items = t.pack(draws, h, w)
+        fld_d = None if fld is None else torch.from_numpy(fld).cuda()
+        items_d = None if items is None else torch.from_numpy(items).cuda()
+        ws = ops.corrupt_workspace(b, h, w)
+        ev1 = StreamingEvaluator(C, ("x",), auroc_bins=512, ensemble_weights=(0.3, 0.9), temperature=1.7)
+        ev2 = StreamingEvaluator(C, ("x",), auroc_bins=512, ensemble_weights=(0.3, 0.9), temperature=1.7)
+        out1, out2 = torch.empty_like(imgs), torch.empty_like(imgs)
+        ev1.update_corrupted("x", imgs, prm, fld_d, items_d, out1, ws, la, lb, lab)
+        ops.corrupt(imgs, prm, fld_d, items_d, out=out2, workspace=ws)
+        ev2.update("x", la, lb, lab)
+        assert torch.equal(out1, out2) and torch.equal(ev1.bins, ev2.bins)
+        assert int(ev1.bins.sum()) > 0
