@@ -78,6 +78,9 @@ _SIGNATURES = {
     "awx_corrupt_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "awx_corrupt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                               C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "awx_corrupt_normalized": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p]),
     "awx_corrupt_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.POINTER(ScoreConfig), C.c_void_p, C.POINTER(ScoreMaps), C.c_void_p]),

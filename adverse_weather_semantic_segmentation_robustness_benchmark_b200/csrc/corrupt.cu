@@ -13,6 +13,8 @@
 //   night: fp32 dim + colour shift, then fp64 noise add                                 :213-225
 //   rain / snow: fp32 throughout, OpenCV-style separable Gaussian                       :135-168, :180-202
 //   final: clip to [0,1], times 255, truncate toward zero
+#include <cuda_bf16.h>
+
 #include "awx_internal.cuh"
 #include "raster.cuh"
 
@@ -42,6 +44,24 @@ __device__ __forceinline__ unsigned to_u8_f64(double v) {
 __device__ __forceinline__ unsigned to_u8_f32(float v) {
   v = fminf(fmaxf(v, 0.0f), 1.0f);
   return (unsigned)__float2int_rz(__fmul_rn(v, 255.0f));
+}
+
+// Optional fused epilogue: albumentations Normalize + ToTensorV2 (data/loader.py:196-199) of the corrupted
+// frame, written as CHW fp32 / bf16 next to (or instead of) the uint8 HWC frame.
+struct NormOut {
+  void* ptr;      // [B,3,H,W]; nullptr = no normalised output
+  int bf16;
+  float mean[3];  // mean * 255
+  float rden[3];  // 1 / (std * 255)
+};
+__device__ __forceinline__ float norm_value(const NormOut& n, unsigned u8, int c) {
+  return __fmul_rn(__fsub_rn((float)u8, n.mean[c]), n.rden[c]);
+}
+__device__ __forceinline__ void norm_store1(const NormOut& n, size_t idx, float v) {
+  if (n.bf16)
+    static_cast<__nv_bfloat16*>(n.ptr)[idx] = __float2bfloat16_rn(v);
+  else
+    static_cast<float*>(n.ptr)[idx] = v;
 }
 
 // -------------------------------------------------------------------------- overlay mask
@@ -76,7 +96,8 @@ template <typename FT>
 __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t* __restrict__ img,
                                                                    uint8_t* __restrict__ out,
                                                                    const AwxCorruptParams* __restrict__ params,
-                                                                   const FT* __restrict__ field, long long HW) {
+                                                                   const FT* __restrict__ field, long long HW,
+                                                                   const __grid_constant__ NormOut norm) {
   const int b = blockIdx.y;
   const AwxCorruptParams prm = params[b];
   if (prm.kind != AWX_CLEAN && prm.kind != AWX_FOG && prm.kind != AWX_NIGHT) return;
@@ -85,7 +106,7 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
   __shared__ float s_unit[256];
   build_unit_table(s_unit);
   const uint8_t* src = img + (size_t)b * HW * 3;
-  uint8_t* dst = out + (size_t)b * HW * 3;
+  uint8_t* dst = out ? out + (size_t)b * HW * 3 : nullptr;
   const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
   const long long nchunks = (HW + kChunkPx - 1) / kChunkPx;
   const FT* fld = field ? field + prm.field_offset : nullptr;
@@ -145,8 +166,33 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
       s_out[threadIdx.x * 3] = wv[0];
       s_out[threadIdx.x * 3 + 1] = wv[1];
       s_out[threadIdx.x * 3 + 2] = wv[2];
+      if (norm.ptr) {  // fused Normalize + CHW: 4 pixels -> one vector per channel plane
+        const bool vec4 = (HW & 3) == 0 && p + 3 < npx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = j * 3 + c;
+            v[j] = norm_value(norm, (wv[k >> 2] >> ((k & 3) * 8)) & 0xffu, c);
+          }
+          const size_t o = ((size_t)b * 3 + c) * HW + px0 + p;
+          if (vec4 && !norm.bf16) {
+            *reinterpret_cast<float4*>(static_cast<float*>(norm.ptr) + o) = make_float4(v[0], v[1], v[2], v[3]);
+          } else if (vec4) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const unsigned*>(&lo);
+            pk.y = *reinterpret_cast<const unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(norm.ptr) + o) = pk;
+          } else {
+            for (int j = 0; j < 4 && p + j < npx; ++j) norm_store1(norm, o + j, v[j]);
+          }
+        }
+      }
     }
     __syncthreads();
+    if (!dst) continue;
     if (full) {
       if (threadIdx.x < kChunkPx * 3 / 16)
         st_stream_u4(dst + px0 * 3 + threadIdx.x * 16, reinterpret_cast<const uint4*>(s_out)[threadIdx.x]);
@@ -181,7 +227,8 @@ constexpr int kHBlock = 12;                          // elements per horizontal-
 template <int R>
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
                                                              const AwxCorruptParams* __restrict__ params,
-                                                             const unsigned* __restrict__ mask, int H, int W, int WW) {
+                                                             const unsigned* __restrict__ mask, int H, int W, int WW,
+                                                             const __grid_constant__ NormOut norm) {
   constexpr int PH = kTileH + 2 * R;
   const int b = blockIdx.z;
   const AwxCorruptParams prm = params[b];
@@ -196,7 +243,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
 
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const uint8_t* src = img + (size_t)b * H * W * 3;
-  uint8_t* dst = out + (size_t)b * H * W * 3;
+  uint8_t* dst = out ? out + (size_t)b * H * W * 3 : nullptr;
   const unsigned* m = mask + (size_t)b * H * WW;
   const bool rain = prm.kind == AWX_RAIN;
   const float k1 = prm.f0, k2 = prm.f1;  // rain: x*k1 + k2 ; snow: clip(x + k1)
@@ -305,6 +352,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   constexpr int CG = kRowE / 4;  // 96 column groups
   constexpr int VR = 8;          // output rows per task
   const bool st32 = ((W * 3) & 3) == 0 && (((uintptr_t)dst) & 3) == 0;
+  unsigned* s_o = reinterpret_cast<unsigned*>(s_pre);  // [kTileH][CG] packed output bytes (norm epilogue only)
   for (int i = threadIdx.x; i < CG * (kTileH / VR); i += kBlurThreads) {
     const int half = i / CG, cg = i - half * CG;
     const float4* pv = reinterpret_cast<const float4*>(s_h + (half * VR) * kRowE + cg * 4);
@@ -330,14 +378,52 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
       const unsigned o1 = vfilt(c.y, a1.y, b1.y, a2.y, b2.y, a3.y, b3.y);
       const unsigned o2 = vfilt(c.z, a1.z, b1.z, a2.z, b2.z, a3.z, b3.z);
       const unsigned o3 = vfilt(c.w, a1.w, b1.w, a2.w, b2.w, a3.w, b3.w);
-      uint8_t* d = dst + ((size_t)(y0 + ry) * W + x0) * 3 + cg * 4;
-      if (st32 && cg * 4 + 3 < tw3) {
-        *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
-      } else {
-        const unsigned ob[4] = {o0, o1, o2, o3};
+      const unsigned ob[4] = {o0, o1, o2, o3};
+      // fused Normalize + CHW: park the packed bytes in shared memory (s_pre is dead by now); the plane
+      // writes below need 4 pixels of ONE channel per thread to be vector stores
+      if (norm.ptr) s_o[ry * CG + cg] = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+      if (dst) {
+        uint8_t* d = dst + ((size_t)(y0 + ry) * W + x0) * 3 + cg * 4;
+        if (st32 && cg * 4 + 3 < tw3) {
+          *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (cg * 4 + k < tw3) d[k] = (uint8_t)ob[k];
+          for (int k = 0; k < 4; ++k)
+            if (cg * 4 + k < tw3) d[k] = (uint8_t)ob[k];
+        }
+      }
+    }
+  }
+  if (norm.ptr) {
+    __syncthreads();
+    // thread task = 4 consecutive pixels of one row: 12 bytes = words 3q..3q+2 (conflict free), one 16-byte
+    // (fp32) or 8-byte (bf16) store per channel plane
+    const int tw = min(kTileW, W - x0);
+    const bool vec4 = (W & 3) == 0;
+    for (int i = threadIdx.x; i < th * (kTileW / 4); i += kBlurThreads) {
+      const int ry = i / (kTileW / 4), q = i - ry * (kTileW / 4);
+      if (q * 4 >= tw) continue;
+      const unsigned wv[3] = {s_o[ry * CG + 3 * q], s_o[ry * CG + 3 * q + 1], s_o[ry * CG + 3 * q + 2]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = j * 3 + c;
+          v[j] = norm_value(norm, (wv[k >> 2] >> ((k & 3) * 8)) & 0xffu, c);
+        }
+        const size_t o = (((size_t)b * 3 + c) * H + (y0 + ry)) * W + x0 + q * 4;
+        if (vec4 && q * 4 + 3 < tw && !norm.bf16) {
+          *reinterpret_cast<float4*>(static_cast<float*>(norm.ptr) + o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else if (vec4 && q * 4 + 3 < tw) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const unsigned*>(&lo);
+          pk.y = *reinterpret_cast<const unsigned*>(&hi);
+          *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(norm.ptr) + o) = pk;
+        } else {
+          for (int j = 0; j < 4 && q * 4 + j < tw; ++j) norm_store1(norm, o + j, v[j]);
+        }
       }
     }
   }
@@ -350,11 +436,11 @@ constexpr size_t blur_smem() {
 
 template <int R>
 int launch_blur(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparams, const unsigned* mask, int64_t B, int H,
-                int W, int WW, cudaStream_t s) {
+                int W, int WW, const NormOut& norm, cudaStream_t s) {
   auto kern = blur_kernel<R>;
   AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem<R>()));
   dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, (unsigned)B);
-  kern<<<grid, kBlurThreads, blur_smem<R>(), s>>>(img, out, dparams, mask, H, W, WW);
+  kern<<<grid, kBlurThreads, blur_smem<R>(), s>>>(img, out, dparams, mask, H, W, WW, norm);
   AWX_CUDA(cudaGetLastError());
   note_launch();
   return AWX_OK;
@@ -416,12 +502,13 @@ extern "C" size_t awx_corrupt_workspace_bytes(int64_t batch, int32_t height, int
   return params_bytes(batch) + (size_t)batch * height * ww * sizeof(unsigned);
 }
 
-extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int32_t H, int32_t W,
-                           const AwxCorruptParams* params, const void* field, int32_t field_dtype, const int32_t* items,
-                           int64_t n_items, void* workspace, void* stream) {
+namespace {
+int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t batch, int32_t H, int32_t W,
+                 const AwxCorruptParams* params, const void* field, int32_t field_dtype, const int32_t* items,
+                 int64_t n_items, void* workspace, void* stream) {
   AWX_REQUIRE(batch >= 0 && H >= 0 && W >= 0, AWX_E_ARG, "awx_corrupt: negative size");
   if (batch == 0 || H == 0 || W == 0) return AWX_OK;
-  AWX_REQUIRE(img && out && params && workspace, AWX_E_ARG, "awx_corrupt: NULL pointer (img/out/params/workspace)");
+  AWX_REQUIRE(img && (out || norm.ptr) && params && workspace, AWX_E_ARG, "awx_corrupt: NULL pointer (img/out/params/workspace)");
   AWX_REQUIRE(batch <= 65535, AWX_E_UNSUPPORTED, "awx_corrupt: batch %lld > 65535 per call", (long long)batch);
   AWX_REQUIRE(field_dtype == AWX_F32 || field_dtype == AWX_F64, AWX_E_ARG, "awx_corrupt: unknown field dtype %d", field_dtype);
   bool any_point = false, any_overlay = false, blur3 = false, blur7 = false;
@@ -458,9 +545,9 @@ extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int3
     const long long cap = (long long)sm_count() * 16;
     dim3 grid((unsigned)(chunks < cap ? chunks : cap), (unsigned)batch);
     if (field_dtype == AWX_F64)
-      pointwise_kernel<double><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW);
+      pointwise_kernel<double><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW, norm);
     else
-      pointwise_kernel<float><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const float*>(field), HW);
+      pointwise_kernel<float><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const float*>(field), HW, norm);
     AWX_CUDA(cudaGetLastError());
   note_launch();
   }
@@ -472,12 +559,38 @@ extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int3
     AWX_CUDA(cudaGetLastError());
   note_launch();
     int rc = AWX_OK;
-    if (blur3) rc = launch_blur<1>(img, out, dparams, mask, batch, H, W, WW, s);
+    if (blur3) rc = launch_blur<1>(img, out, dparams, mask, batch, H, W, WW, norm, s);
     if (rc != AWX_OK) return rc;
-    if (blur7) rc = launch_blur<3>(img, out, dparams, mask, batch, H, W, WW, s);
+    if (blur7) rc = launch_blur<3>(img, out, dparams, mask, batch, H, W, WW, norm, s);
     if (rc != AWX_OK) return rc;
   }
   return AWX_OK;
+}
+}  // namespace
+
+extern "C" int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int32_t H, int32_t W,
+                           const AwxCorruptParams* params, const void* field, int32_t field_dtype, const int32_t* items,
+                           int64_t n_items, void* workspace, void* stream) {
+  AWX_REQUIRE(batch == 0 || H == 0 || W == 0 || out != nullptr, AWX_E_ARG, "awx_corrupt: out is NULL");
+  NormOut norm{};
+  return corrupt_impl(img, out, norm, batch, H, W, params, field, field_dtype, items, n_items, workspace, stream);
+}
+
+extern "C" int awx_corrupt_normalized(const uint8_t* img, uint8_t* out, void* norm_out, int32_t norm_dtype,
+                                      const float* mean255, const float* rdenom, int64_t batch, int32_t H, int32_t W,
+                                      const AwxCorruptParams* params, const void* field, int32_t field_dtype,
+                                      const int32_t* items, int64_t n_items, void* workspace, void* stream) {
+  AWX_REQUIRE(batch == 0 || H == 0 || W == 0 || (norm_out && mean255 && rdenom), AWX_E_ARG,
+              "awx_corrupt_normalized: NULL pointer (norm_out/mean255/rdenom)");
+  AWX_REQUIRE(norm_dtype == AWX_F32 || norm_dtype == AWX_BF16, AWX_E_ARG, "awx_corrupt_normalized: norm dtype must be AWX_F32 or AWX_BF16");
+  NormOut norm{};
+  norm.ptr = norm_out;
+  norm.bf16 = norm_dtype == AWX_BF16;
+  for (int c = 0; c < 3 && mean255 && rdenom; ++c) {
+    norm.mean[c] = mean255[c];
+    norm.rden[c] = rdenom[c];
+  }
+  return corrupt_impl(img, out, norm, batch, H, W, params, field, field_dtype, items, n_items, workspace, stream);
 }
 
 namespace awx {

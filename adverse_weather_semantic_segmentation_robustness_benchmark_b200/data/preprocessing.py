@@ -210,6 +210,31 @@ class WeatherDegradationTransforms:
         items_d = None if items is None else torch.from_numpy(items).to(dev)
         return ops.corrupt(img, prm, fld_d, items_d, out=out)
 
+    def corrupt_batch_normalized(self, images, draws: Sequence[WeatherDraw], mean=ops_prep.IMAGENET_MEAN,
+                                 std=ops_prep.IMAGENET_STD, out_dtype: torch.dtype = torch.float32,
+                                 field_dtype=np.float64, keep_u8: bool = False):
+        """corrupt_batch with the dataset's Normalize(mean, std) + ToTensorV2 (loader.py:196-199) fused into
+        the corruption kernels: returns the fp32 / bf16 [B,3,H,W] tensor the backbones consume (and the
+        uint8 frames too when ``keep_u8``), in one pass over HBM."""
+        dev = ops.require_cuda()
+        img = torch.from_numpy(np.ascontiguousarray(images)) if isinstance(images, np.ndarray) else images
+        if img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3:
+            raise ValueError(f"images must be uint8 [B,H,W,3], got {img.dtype} {tuple(img.shape)}")
+        img = ops.to_device(img)
+        b, h, w, _ = img.shape
+        if len(draws) != b:
+            raise ValueError(f"{len(draws)} draws for {b} frames")
+        for d in draws:
+            if d.kind == "fog" and d.depth is None:
+                d.depth = self.synthetic_depth(d.depth_noise)[0].cpu().numpy()
+        prm, fld, items = self.pack(draws, h, w, field_dtype)
+        fld_d = None if fld is None else torch.from_numpy(fld).to(dev)
+        items_d = None if items is None else torch.from_numpy(items).to(dev)
+        norm = torch.empty((b, 3, h, w), dtype=out_dtype, device=dev)
+        u8 = ops.corrupt(img, prm, fld_d, items_d, norm_out=norm,
+                         norm_params=ops_prep.normalize_params(mean, std), write_u8=keep_u8)
+        return (norm, u8) if keep_u8 else norm
+
     # ------------------------------------------------------------------ reference signatures
     def apply_weather_effect(self, image: np.ndarray, weather_type: str,
                              intensity: Optional[float] = None) -> np.ndarray:

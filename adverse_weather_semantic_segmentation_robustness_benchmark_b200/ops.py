@@ -240,10 +240,14 @@ def corrupt_workspace(batch: int, height: int, width: int) -> torch.Tensor:
 
 def corrupt(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tensor] = None,
             items: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-            workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+            workspace: Optional[torch.Tensor] = None, norm_out: Optional[torch.Tensor] = None,
+            norm_params=None, write_u8: bool = True):
     """awx_corrupt on a device-resident uint8 [B,H,W,3] batch.  `params`: host records
     (``_lib.CORRUPT_PARAMS_DTYPE``); `field`: device fp32/fp64 depth / noise values; `items`:
-    device int32 [n,5] drops / flakes."""
+    device int32 [n,5] drops / flakes.
+    With `norm_out` (fp32 / bf16 [B,3,H,W]) and `norm_params` = (mean*255, 1/(std*255)) fp32 triples, the
+    dataset's Normalize + ToTensorV2 is fused into the kernels' epilogue (awx_corrupt_normalized);
+    `write_u8=False` then skips the uint8 frame.  Returns `out` (or `norm_out` when write_u8 is False)."""
     lib = _lib.load()
     if not images.is_cuda or images.dtype != torch.uint8 or not images.is_contiguous():
         raise ValueError("images must be a contiguous CUDA uint8 tensor")
@@ -253,7 +257,9 @@ def corrupt(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tens
     if params.dtype != _lib.CORRUPT_PARAMS_DTYPE or len(params) != b:
         raise ValueError("params must be one CORRUPT_PARAMS_DTYPE record per frame")
     params = np.ascontiguousarray(params)
-    if out is None:
+    if not write_u8 and norm_out is None:
+        raise ValueError("write_u8=False needs norm_out")
+    if out is None and write_u8:
         out = torch.empty_like(images)
     if workspace is None:
         workspace = corrupt_workspace(b, h, w)
@@ -270,10 +276,24 @@ def corrupt(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tens
             raise TypeError("items must be int32 [n,5]")
         items = items.contiguous()
         n_items = items.shape[0]
-    rc = lib.awx_corrupt(_ptr(images), _ptr(out), b, h, w, params.ctypes.data_as(C.c_void_p), _ptr(field), fdt,
-                         _ptr(items), n_items, _ptr(workspace), _stream())
-    _lib.check(rc, "awx_corrupt")
-    return out
+    if norm_out is None:
+        rc = lib.awx_corrupt(_ptr(images), _ptr(out), b, h, w, params.ctypes.data_as(C.c_void_p), _ptr(field), fdt,
+                             _ptr(items), n_items, _ptr(workspace), _stream())
+        _lib.check(rc, "awx_corrupt")
+        return out
+    if norm_out.dtype not in (torch.float32, torch.bfloat16) or tuple(norm_out.shape) != (b, 3, h, w) \
+            or not norm_out.is_cuda or not norm_out.is_contiguous():
+        raise ValueError("norm_out must be a contiguous CUDA fp32 / bf16 [B,3,H,W] tensor")
+    m, r = norm_params
+    m = np.ascontiguousarray(m, dtype=np.float32)
+    r = np.ascontiguousarray(r, dtype=np.float32)
+    rc = lib.awx_corrupt_normalized(_ptr(images), _ptr(out) if write_u8 else None, _ptr(norm_out),
+                                    _lib.F32 if norm_out.dtype == torch.float32 else _lib.BF16,
+                                    m.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), b, h, w,
+                                    params.ctypes.data_as(C.c_void_p), _ptr(field), fdt, _ptr(items), n_items,
+                                    _ptr(workspace), _stream())
+    _lib.check(rc, "awx_corrupt_normalized")
+    return out if write_u8 else norm_out
 
 
 def corrupt_score(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tensor], items: Optional[torch.Tensor],

@@ -181,6 +181,16 @@ int awx_corrupt(const uint8_t* img, uint8_t* out, int64_t batch, int32_t height,
                 const AwxCorruptParams* params /*HOST*/, const void* field, int32_t field_dtype,
                 const int32_t* items, int64_t n_items, void* workspace, void* stream);
 
+/* awx_corrupt with the dataset's Normalize(mean, std) + ToTensorV2 (data/loader.py:196-199) fused into the
+ * corruption kernels' epilogue: norm_out [B,3,H,W] fp32 (AWX_F32) or bf16 (AWX_BF16) = (u8 - mean255[c]) * rdenom[c]
+ * of the corrupted frame, the tensor the backbones consume, without a second pass over HBM.
+ * `out` (uint8 HWC) may be NULL when only the normalised tensor is wanted.  mean255 / rdenom: HOST float[3]. */
+int awx_corrupt_normalized(const uint8_t* img, uint8_t* out /*nullable*/, void* norm_out, int32_t norm_dtype,
+                           const float* mean255 /*HOST*/, const float* rdenom /*HOST*/,
+                           int64_t batch, int32_t height, int32_t width,
+                           const AwxCorruptParams* params /*HOST*/, const void* field, int32_t field_dtype,
+                           const int32_t* items, int64_t n_items, void* workspace, void* stream);
+
 /* awx_corrupt followed by awx_score of the same batch (pixels_per_image = height * width) on one stream:
  * one call per weather condition of the evaluation sweep (scripts/evaluate.py:177-212 per batch). */
 int awx_corrupt_score(const uint8_t* img, uint8_t* out, int32_t height, int32_t width,

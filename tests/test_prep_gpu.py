@@ -172,3 +172,31 @@ def test_temperature_grid_large_and_bad_labels(pkg):
     bad[1, 5, 5] = 40
     with pytest.raises(IndexError):
         pkg.ConfidenceCalibration().optimize_temperature(logits, bad)
+
+
+@pytest.mark.parametrize("h,w", [(64, 128), (50, 70), (1024, 2048)])
+def test_corrupt_with_fused_normalize_epilogue(pkg, h, w):
+    """awx_corrupt_normalized == awx_normalize_chw(awx_corrupt(...)) bit for bit, for every kind (both blur
+    sizes, the clean copy, ragged sizes), fp32 and bf16, with and without the uint8 frame."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops_prep
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.data.preprocessing import (
+        WeatherDegradationTransforms)
+    t = WeatherDegradationTransforms(seed=31)
+    rng = np.random.RandomState(h + w)
+    kinds = ["clean", "fog", "rain", "snow", "night", "snow"] if h < 1000 else ["rain", "snow", "fog"]
+    imgs = torch.from_numpy(rng.randint(0, 255, (len(kinds), h, w, 3)).astype(np.uint8)).cuda()
+    draws = [t.draw(k, h, w) for k in kinds]
+    snow = [d for d in draws if d.kind == "snow"]
+    snow[0].blur_k = 3
+    snow[-1].blur_k = 7
+    for d in draws:
+        if d.kind == "fog":
+            d.depth = ow.depth_from_noise(d.depth_noise)
+    want_u8 = t.corrupt_batch(imgs, draws)
+    want = ops_prep.normalize_chw(want_u8)
+    norm, u8 = t.corrupt_batch_normalized(imgs, draws, keep_u8=True)
+    assert torch.equal(u8, want_u8) and torch.equal(norm, want)
+    only = t.corrupt_batch_normalized(imgs, draws)
+    assert torch.equal(only, want)
+    bf = t.corrupt_batch_normalized(imgs, draws, out_dtype=torch.bfloat16)
+    assert bf.dtype == torch.bfloat16 and torch.equal(bf, ops_prep.normalize_chw(want_u8, out_dtype=torch.bfloat16))
