@@ -37,6 +37,7 @@ struct Geo {
   static constexpr int kUnitBytes = kUnitFloats * 4;
 };
 constexpr int kMaxUnits = 5;
+constexpr int kFastEceBins = 15, kFastAurocBins = 4096;  // the streaming evaluator's configuration
 constexpr int kSingleWarps = 19;                // consumer warps of the bins-only single-member kernels
 constexpr unsigned kFlushPixels = 60000;        // per-warp ECE words are flushed before 2^16 pixels
 
@@ -49,8 +50,25 @@ __device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// the same operations on 32-bit shared addresses (the hot loops keep one shared base register and add
+// immediates; converting a generic pointer costs an S2R + LEA every time)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
   unsigned ok;
@@ -192,7 +210,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   constexpr bool ENS = MODE != 0;
   constexpr int NP = (kC + 1) / 2;  // 10 class pairs
   constexpr float kDummy = -1e30f;
-  const int nb = p.nb, NB = p.auroc_bins;
+  // bins-only kernels: 15 ECE bins and 4096 (ensemble) / 0 (single) AUROC bins are compile-time constants, so
+  // every shared-memory offset below is an immediate (launch_v2_mode checks the configuration)
+  const int nb = FAST != 0 ? kFastEceBins : p.nb;
+  const int NB = FAST != 0 ? (ENS ? kFastAurocBins : 0) : p.auroc_bins;
   const bool have_labels = FAST != 0 || p.labels != nullptr;
   extern __shared__ __align__(128) unsigned char smem[];
   u64* full = reinterpret_cast<u64*>(smem);              // [kMaxUnits]
@@ -279,7 +300,8 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   unsigned* my_hi = w_hi + warp * nb;
   const uint32_t conf_sa = smem_u32(s_conf), auroc_sa = smem_u32(s_auroc), cc_sa = smem_u32(my_cc);
   const uint32_t ece_stride = (uint32_t)(kConsWarps * nb * 4);  // my_cc -> my_lo -> my_hi
-  const float* my_units = units + t;
+  const uint32_t sbase = smem_u32(smem);                                  // full[u] at sbase + 8u, empty[u] at + 8(kMaxUnits + u)
+  const uint32_t my_unit0 = sbase + (uint32_t)v2_ring_offset(kConsWarps, nb, NB) + 4u * (uint32_t)t;
   // B * HW < 2^32 (score_v2_supported): all pixel and tile indices of the consumers are 32 bit
   const unsigned HWu = (unsigned)HW, tpiu = (unsigned)tpi, ntu = (unsigned)ntiles;
   unsigned img = blockIdx.x / tpiu, tin = blockIdx.x - img * tpiu;
@@ -303,30 +325,30 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     // ---- pull the pixel's 19 (+19) values into registers, release the ring units at once
     float2 a[NP], b[ENS ? NP : 1];
     {
-      mbar_wait(full + u, ph);
-      const float* s = my_units + (size_t)u * kUnitFloats;
+      mbar_wait_a(sbase + 8u * u, ph);
+      const uint32_t s = my_unit0 + u * (uint32_t)G::kUnitBytes;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        a[i].x = s[(2 * i) * kTP];
-        a[i].y = (2 * i + 1 < kC) ? s[(2 * i + 1) * kTP] : kDummy;
+        a[i].x = lds_f32(s + (2 * i) * kTP * 4);
+        a[i].y = (2 * i + 1 < kC) ? lds_f32(s + (2 * i + 1) * kTP * 4) : kDummy;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty + u);
+      if (lane == 0) mbar_arrive_a(sbase + 8u * (kMaxUnits + u));
       if (++u == (unsigned)NU) {
         u = 0;
         ph ^= 1u;
       }
     }
     if (ENS) {
-      mbar_wait(full + u, ph);
-      const float* s = my_units + (size_t)u * kUnitFloats;
+      mbar_wait_a(sbase + 8u * u, ph);
+      const uint32_t s = my_unit0 + u * (uint32_t)G::kUnitBytes;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        b[ENS ? i : 0].x = s[(2 * i) * kTP];
-        b[ENS ? i : 0].y = (2 * i + 1 < kC) ? s[(2 * i + 1) * kTP] : kDummy;
+        b[ENS ? i : 0].x = lds_f32(s + (2 * i) * kTP * 4);
+        b[ENS ? i : 0].y = (2 * i + 1 < kC) ? lds_f32(s + (2 * i + 1) * kTP * 4) : kDummy;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty + u);
+      if (lane == 0) mbar_arrive_a(sbase + 8u * (kMaxUnits + u));
       if (++u == (unsigned)NU) {
         u = 0;
         ph ^= 1u;
@@ -527,8 +549,16 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
           js = so.js;
           marg = so.mpred;
         } else {
-          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, p.w0, p.w1, div_mode, T, s_edges, nb, &ambig);
+          int amb = 0;
+          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, p.w0, p.w1, div_mode, T, s_edges, nb, &amb);
+          ambig = amb;
           bin = ece_bin(conf, s_edges, nb);
+        }
+        // bookkeeping that only these rare pixels can need: the ambiguity count, and correct pixels that
+        // fall in no ECE bin (every other correct pixel is counted through its bin's packed word)
+        if (have_labels && lab != ignore) {
+          n_ambig += ambig;
+          if (bin < 0 && lab == pred) ++n_correct;
         }
       }
     }
@@ -562,7 +592,6 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       since_flush += 32u;
       const bool valid = act && lab != ignore;
       const bool correct = valid && lab == pred;
-      n_correct += correct;
       int ckey = -1, akey = -1;
       if (valid) {
         // confusion index as torch evaluates targets*C + predictions (uint8 product wraps mod 256)
@@ -572,7 +601,6 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
           ckey = idx;
         else
           ++n_bad;
-        n_ambig += ambig;
         if (ENS && NB > 0) {
           // floor(mi * scale) clamped to [0, NB-1]; NaN -> 0 (fmaxf returns the non-NaN operand)
           const float qv = fminf(fmaxf(mi * p.auroc_scale, 0.f), p.auroc_top);
@@ -600,6 +628,14 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
             }
           }
         }
+      } else if (ckey >= 0 && bin >= 0 && (akey >= 0 || !(ENS && NB > 0))) {
+        // the common case under ONE branch: five reductions, no reconvergence point between them
+        red_add(conf_sa + 4u * ckey, 1u);
+        if (ENS && NB > 0) red_add(auroc_sa + 4u * akey, 1u);
+        const uint32_t ba = cc_sa + 4u * bin;
+        red_add(ba, 1u | (correct ? 0x10000u : 0u));
+        red_add(ba + ece_stride, fx & 0xffffu);
+        red_add(ba + 2u * ece_stride, fx >> 16);
       } else {
         red_add_if(ckey, conf_sa + 4u * ckey, 1u);
         red_add_if(akey, auroc_sa + 4u * akey, 1u);
@@ -632,7 +668,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   unsigned long long* bins = p.bins;
   // the remaining counters follow from the histograms: valid = sum(confusion) + bad,
   // ensemble-wrong = sum(auroc_pos), no-bin = valid - sum(ece_count); pixels are added by the host
-  unsigned part_conf = 0, part_pos = 0, part_ece = 0;
+  unsigned part_conf = 0, part_pos = 0, part_ece = 0, part_cor = 0;
   for (int i = t; i < kC * kC; i += kCons) {
     const unsigned c = s_conf[i];
     part_conf += c;
@@ -652,6 +688,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       sum += w_sum64[w * nb + i] + ((u64)w_hi[w * nb + i] << 16) + w_lo[w * nb + i];
     }
     part_ece += (unsigned)cnt;
+    part_cor += (unsigned)cor;
     if (cnt) {
       atomicAdd(bins + p.lay.ece_count + i, cnt);
       if (cor) atomicAdd(bins + p.lay.ece_correct + i, cor);
@@ -663,7 +700,9 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     const unsigned sc = __reduce_add_sync(0xffffffffu, part_conf);
     const unsigned sp = __reduce_add_sync(0xffffffffu, part_pos);
     const unsigned se = __reduce_add_sync(0xffffffffu, part_ece);
+    const unsigned sr = __reduce_add_sync(0xffffffffu, part_cor);
     if (lane == 0) {
+      if (sr) atomicAdd(&s_cnt[AWX_CNT_CORRECT], sr);  // correct pixels counted through their ECE bins
       if (sc) atomicAdd(&s_cnt[AWX_CNT_VALID], sc);
       if (sp) atomicAdd(&s_cnt[AWX_CNT_ENS_WRONG], sp);
       if (se) atomicAdd(&s_cnt[AWX_CNT_NO_BIN], se);  // holds sum(ece_count) until the fix-up below
@@ -736,7 +775,8 @@ bool uniform_edges(const ScoreParams& p) {
 template <int MODE>
 int launch_v2_mode(const ScoreParams& p, bool js, cudaStream_t stream) {
   const bool maps = p.pred || p.fused || p.conf || p.mi || p.js;
-  if (!maps && p.labels != nullptr && !js && !p.debug_skip && uniform_edges(p))
+  if (!maps && p.labels != nullptr && !js && !p.debug_skip && uniform_edges(p) && p.nb == kFastEceBins &&
+      p.auroc_bins == (MODE != 0 ? kFastAurocBins : 0))
     return p.label_mode == AWX_LABEL_U8 ? launch_v2_fast<MODE, 1>(p, stream) : launch_v2_fast<MODE, 2>(p, stream);
   if (MODE != 0 && js) return launch_v2<MODE, (MODE != 0), 0, -1, 15>(p, stream);
   return launch_v2<MODE, false, 0, -1, 15>(p, stream);
