@@ -16,6 +16,8 @@
 //  * entropies use H(p) = ln S - (sum e_c d_c)/S (d_c = x_c - max) instead of C logarithms.
 #include <cstdlib>
 
+#include <cstring>
+
 #include "score_common.cuh"
 
 namespace awx {
@@ -322,6 +324,14 @@ __global__ void __launch_bounds__(256) variance_kernel(const float* __restrict__
 
 using namespace awx;
 
+// The branch-free quotient x * RN(1/T) corrected by one FMA residual step is the correctly rounded x / T for
+// every divisor except those whose significand is all ones (Markstein); such a T takes the true division.
+static bool all_ones_significand(float t) {
+  uint32_t u;
+  memcpy(&u, &t, sizeof(u));
+  return (u & 0x7fffffu) == 0x7fffffu;
+}
+
 extern "C" int awx_bins_layout(int32_t C, int32_t nb, int32_t NB, AwxBinsLayout* out) {
   AWX_REQUIRE(out != nullptr, AWX_E_ARG, "awx_bins_layout: out is NULL");
   AWX_REQUIRE(C >= 1 && C <= AWX_MAX_CLASSES, AWX_E_UNSUPPORTED, "num_classes %d outside 1..%d", C, AWX_MAX_CLASSES);
@@ -371,7 +381,7 @@ extern "C" int awx_score(const float* logits_a, const float* logits_b, const voi
   const bool want_fused = maps && maps->fused;
   if (!cfg->use_temperature || cfg->temperature == 1.0f)
     p.div_mode = 0;
-  else if (cfg->temperature > 0.f && std::isfinite(cfg->temperature) && !want_fused)
+  else if (cfg->temperature > 0.f && std::isfinite(cfg->temperature) && !want_fused && !all_ones_significand(cfg->temperature))
     p.div_mode = 1;
   else
     p.div_mode = 2;
