@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--sweep-frames", type=int, default=0,
+                    help="BASELINE configs[4]: evaluation sweep over this many frames in total (e.g. 10000), sharded "
+                         "over the ranks, one all_reduce at the end; prints its own JSON line and exits")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -374,6 +377,75 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_sweep(args, rank, world, local_rank):
+    """BASELINE configs[4]: N frames in total, frame i -> rank i mod world (batches of --batch frames cycled from
+    the rank's pool of pre-drawn frames / parameters), every batch corrupted under one condition (cycling through
+    the five) and scored into that condition's bins; ONE all_reduce of the packed bins closes the sweep.
+    Strong scaling: the total number of frames is fixed."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import _lib
+    lib = _lib.load()
+    wl = Workload(args, rank, device)
+    mine = len(range(rank, args.sweep_frames, world))
+    batches = [(args.batch if (i + 1) * args.batch <= mine else mine - i * args.batch)
+               for i in range((mine + args.batch - 1) // args.batch)]
+
+    def sweep():
+        wl.ev.reset()
+        for i, nb in enumerate(batches):
+            kind = CONDITIONS[i % len(CONDITIONS)]
+            if kind != "clean":
+                wl.ops.corrupt(wl.images[:nb], wl.params[kind][:nb], wl.fields[kind], wl.items[kind], out=wl.out[:nb],
+                               workspace=wl.workspace)
+            wl.ev.update(kind, wl.la[:nb], wl.lb[:nb], wl.labels[:nb])
+        wl.ev.all_reduce()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sweep()  # warm-up
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.awx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sweep()
+    e1.record()
+    barrier()
+    launches = lib.awx_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    res = wl.ev.finalize()
+    if rank == 0:
+        px = float(args.sweep_frames) * args.height * args.width
+        cfg = workload_config(args)
+        cfg["workload"] = ("configs[4]: %d-frame synthetic Cityscapes eval sweep, frame i -> rank i mod %d, batches of %d "
+                           "frames cycled from a per-rank pool, one condition per batch, one all_reduce of the bins"
+                           % (args.sweep_frames, world, args.batch))
+        print(json.dumps({
+            "metric": METRIC, "value": px / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": 1, "warmup": 1,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic", "config": cfg, "frames": args.sweep_frames, "frames_per_s": args.sweep_frames / (ms * 1e-3),
+            "gpu_launches": int(launches), "clocks": clocks,
+            "results": {k: (float(v) if v == v else None) for k, v in res.items()},
+            "bins_checksum": int(wl.ev.bins.sum().item())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_e2e(args, wl, device, world, barrier, max_over_ranks, px_step):
     """Same step, but every input starts in (pinned) host memory and the bins are read back."""
     import torch
@@ -454,6 +526,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.sweep_frames > 0:
+        run_sweep(args, rank, world, local_rank)
+        return
     run_gpu_arm(args, rank, world, local_rank)
 
 
