@@ -17,6 +17,7 @@
 
 #include "awx_internal.cuh"
 #include "raster.cuh"
+#include "convert.cuh"
 
 namespace awx {
 namespace {
@@ -31,10 +32,6 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   if (n == 1) return 0;
   while (i < 0 || i >= n) i = i < 0 ? -i : 2 * n - 2 - i;
   return i;
-}
-
-__device__ __forceinline__ void build_unit_table(float* lut) {
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
 }
 
 __device__ __forceinline__ unsigned to_u8_f64(double v) {
@@ -103,8 +100,6 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
   if (prm.kind != AWX_CLEAN && prm.kind != AWX_FOG && prm.kind != AWX_NIGHT) return;
   __shared__ __align__(16) unsigned s_in[kChunkPx * 3 / 4];
   __shared__ __align__(16) unsigned s_out[kChunkPx * 3 / 4];
-  __shared__ float s_unit[256];
-  build_unit_table(s_unit);
   const uint8_t* src = img + (size_t)b * HW * 3;
   uint8_t* dst = out ? out + (size_t)b * HW * 3 : nullptr;
   const bool aligned = (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
@@ -146,7 +141,7 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
           for (int c = 0; c < 3; ++c) {
             const int k = j * 3 + c;  // byte index within the 12
             const unsigned u = (wv[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-            const float x = s_unit[u];
+            const float x = unit_of_u8(u);
             unsigned r;
             if (prm.kind == AWX_FOG) {
               r = to_u8_f64(__dadd_rn(__dmul_rn((double)x, tr), veil));
@@ -237,9 +232,6 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   extern __shared__ __align__(16) unsigned char smem[];
   float* s_pre = reinterpret_cast<float*>(smem);  // [PH][kPreW] point-op'ed, overlaid, fp32
   float* s_h = s_pre + PH * kPreW;                // [PH][kRowE] after the horizontal pass
-  __shared__ float s_unit[256];
-  build_unit_table(s_unit);
-  __syncthreads();
 
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const uint8_t* src = img + (size_t)b * H * W * 3;
@@ -250,7 +242,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   const bool vec_ok = ((W * 3) & 15) == 0 && (((uintptr_t)src) & 15) == 0;
 
   auto point = [&](unsigned u8, int c, bool over) -> float {
-    const float x = s_unit[u8];
+    const float x = unit_of_u8(u8);
     if (rain) {
       const float v = __fadd_rn(__fmul_rn(x, k1), k2);
       return over ? (c == 0 ? 0.8f : (c == 1 ? 0.9f : 1.0f)) : v;

@@ -3,6 +3,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "raster.cuh"
+#include "convert.cuh"
 
 extern "C" void raster_lines(const int32_t* items, int n, int H, int W, uint8_t* mask) {
   auto emit = [&](int y, int x0, int x1) {
@@ -22,4 +23,8 @@ extern "C" void raster_discs(const int32_t* items, int n, int H, int W, uint8_t*
     const int32_t* it = items + 5 * i;
     awx::raster::disc(it[0], it[1], it[2], W, H, emit);
   }
+}
+
+extern "C" void unit_table(float* out256) {
+  for (unsigned u = 0; u < 256; ++u) out256[u] = awx::unit_of_u8(u);
 }

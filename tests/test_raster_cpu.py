@@ -25,7 +25,7 @@ CSRC = os.path.join(ROOT, "adverse_weather_semantic_segmentation_robustness_benc
 @pytest.fixture(scope="module")
 def lib():
     os.makedirs(OUT_DIR, exist_ok=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, SRC, "-o", OUT], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-I", CSRC, SRC, "-o", OUT], check=True)
     l = ctypes.CDLL(OUT)
     for fn in (l.raster_lines, l.raster_discs):
         fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -116,3 +116,11 @@ def test_discs_exhaustive(lib):
     assert m.sum(1)[13:18].tolist() == [1, 3, 5, 3, 1]
     m = _ours(lib.raster_discs, np.array([[15, 15, 8, 0, 0]], np.int32), h, w)
     assert m.sum(1)[7:24].tolist() == [1, 7, 11, 13, 13, 15, 15, 15, 17, 15, 15, 15, 13, 13, 11, 7, 1]
+
+
+def test_unit_of_u8(lib):
+    """csrc/convert.cuh: the table-free u8 -> fp32 conversion equals astype(float32) / 255 for every byte."""
+    import ctypes as C
+    out = np.zeros(256, np.float32)
+    lib.unit_table(out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, np.arange(256, dtype=np.uint8).astype(np.float32) / np.float32(255.0))
