@@ -214,3 +214,41 @@ def test_normalize_params_are_fp32_albumentations_scalars():
     assert m.dtype == np.float32 and r.dtype == np.float32
     assert np.array_equal(m, np.array(ops_prep.IMAGENET_MEAN, np.float32) * np.float32(255.0))
     assert np.array_equal(r, np.float32(1) / (np.array(ops_prep.IMAGENET_STD, np.float32) * np.float32(255.0)))
+
+
+def test_argument_errors_of_the_prep_entry_points(lib):
+    """Every 8f-row entry point validates its arguments before touching CUDA: empty inputs are no-ops,
+    NULL pointers / bad dtypes / bad sizes return AWX_E_ARG or AWX_E_UNSUPPORTED with a message."""
+    h = lib.load()
+    E_ARG, E_UNSUP = -1, -2
+    f3 = (ctypes.c_float * 3)(1, 2, 3)
+    assert h.awx_normalize_chw(None, None, lib.F32, 0, 8, 8, f3, f3, None) == 0
+    assert h.awx_normalize_chw(None, None, lib.F32, 1, 8, 8, f3, f3, None) == E_ARG
+    assert b"NULL pointer" in h.awx_last_error()
+    assert h.awx_normalize_chw(None, None, lib.F64, 1, 8, 8, f3, f3, None) == E_ARG
+    assert h.awx_style_transfer(None, None, 0, 1.0, 0.0, 0.0, 0, None) == 0
+    assert h.awx_style_transfer(None, None, 4, 1.0, 0.0, 0.0, 0, None) == E_ARG
+    assert h.awx_temperature_workspace_bytes(100) > 0 and h.awx_temperature_workspace_bytes(0) == 0
+    assert h.awx_temperature_workspace_bytes(129) == 0
+    t = (ctypes.c_float * 2)(1.0, -1.0)
+    assert h.awx_temperature_nll(None, None, lib.LABEL_I64, 0, 19, 255, t, 2, None, None, None) == 0
+    assert h.awx_temperature_nll(None, None, lib.LABEL_I64, 4, 19, 255, t, 2, None, None, None) == E_ARG
+    assert h.awx_temperature_nll(None, None, lib.LABEL_I64, 4, 65, 255, t, 2, None, None, None) == E_UNSUP
+    assert h.awx_temperature_nll(None, None, lib.LABEL_I64, 4, 19, 255, t, 500, None, None, None) == E_UNSUP
+    assert h.awx_fog_density_workspace_bytes(0) == 0 and h.awx_fog_density_workspace_bytes(2) >= 2 * (4096 * 3 * 4)
+    assert h.awx_local_contrast(None, lib.U8, None, 0, 8, 8, 0, 0, None, None, None) == 0
+    assert h.awx_local_contrast(None, lib.U8, None, 1, 8, 8, 0, 0, None, None, None) == E_ARG
+    assert h.awx_fog_density_finish(None, None, lib.F64, None, None, 0, 64, None, None) == 0
+    assert h.awx_fog_density_finish(None, None, lib.F64, None, None, 1, 64, None, None) == E_ARG
+    assert h.awx_estimate_depth(None, None, None, 0, 8, 8, None, 8, None, None) == 0
+    assert h.awx_estimate_depth(None, None, None, 1, 8, 8, None, 8, None, None) == E_ARG
+    assert h.awx_corrupt_normalized(None, None, None, lib.F32, None, None, 1, 8, 8, None, None, lib.F64, None, 0, None, None) == E_ARG
+    assert h.awx_corrupt_normalized(None, None, None, lib.F32, None, None, 0, 8, 8, None, None, lib.F64, None, 0, None, None) == 0
+
+
+def test_evaluate_model_signature_matches_the_reference():
+    import inspect
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import evaluate_model
+    params = list(inspect.signature(evaluate_model).parameters)
+    assert params[:5] == ["model", "test_loader", "metrics", "device", "config"]   # scripts/evaluate.py:134-140
+    assert evaluate_model(object(), [], None, None, None) == {}                     # empty loader: no device needed
