@@ -39,7 +39,8 @@ struct Geo {
 constexpr int kMaxUnits = 5;
 constexpr int kFastEceBins = 15, kFastAurocBins = 4096;  // the streaming evaluator's configuration
 constexpr int kSingleWarps = 19;                // consumer warps of the bins-only single-member kernels
-constexpr unsigned kFlushPixels = 60000;        // per-warp ECE words are flushed before 2^16 pixels
+constexpr unsigned kFlushPixels = 60000;        // per-warp confidence sums are flushed before 2^16 pixels
+constexpr int kEceRep = 4;                      // replicas (lane & 3) of the per-warp confidence-sum words
 
 typedef unsigned long long u64;
 
@@ -151,7 +152,7 @@ __device__ __forceinline__ int ece_bin_fast(float conf, const float* e, int nb) 
 // byte offset of the TMA ring inside dynamic shared memory (everything before it is bookkeeping)
 __host__ __device__ inline size_t v2_ring_offset(int cons_warps, int nb, int NB) {
   size_t o = 2 * kMaxUnits * sizeof(u64) + (8 + 368) * 4 + (AWX_MAX_ECE_BINS + 4) * 4;
-  o += (size_t)cons_warps * nb * 36 + (size_t)2 * NB * 4;
+  o += (size_t)cons_warps * nb * (2 + 2 * kEceRep) * 4 + (size_t)2 * NB * 4;
   return (o + 127) & ~(size_t)127;
 }
 
@@ -221,20 +222,22 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   unsigned* s_cnt = reinterpret_cast<unsigned*>(empty + kMaxUnits);  // [8]
   unsigned* s_conf = s_cnt + 8;                          // [368] (361 used)
   float* s_edges = reinterpret_cast<float*>(s_conf + 368);           // [AWX_MAX_ECE_BINS + 4] (keeps the u64 arrays 8-byte aligned)
-  u64* w_cnt64 = reinterpret_cast<u64*>(s_edges + AWX_MAX_ECE_BINS + 4);  // [warps][nb]
-  u64* w_cor64 = w_cnt64 + kConsWarps * nb;
-  u64* w_sum64 = w_cor64 + kConsWarps * nb;
-  unsigned* w_cc = reinterpret_cast<unsigned*>(w_sum64 + kConsWarps * nb);  // [warps][nb] count | correct << 16
-  unsigned* w_lo = w_cc + kConsWarps * nb;
-  unsigned* w_hi = w_lo + kConsWarps * nb;
-  unsigned* s_auroc = w_hi + kConsWarps * nb;            // [2*NB]
+  // per-warp ECE words.  Counts take the value 1 (the hardware aggregates lanes hitting the same word:
+  // ATOMS.POPC.INC, ~3 wavefronts); the confidence sums carry per-lane values, and a shared-memory atomic add
+  // whose lanes collide on one address is serialised lane by lane (measured: 28 wavefronts per instruction with
+  // ~10 lanes per bin), so every (warp, bin) sum has kEceRep replicas selected by lane & 3.
+  unsigned* w_cnt = reinterpret_cast<unsigned*>(s_edges + AWX_MAX_ECE_BINS + 4);  // [warps][nb]
+  unsigned* w_cor = w_cnt + kConsWarps * nb;                                      // [warps][nb]
+  unsigned* w_lo = w_cor + kConsWarps * nb;                                       // [warps][nb][kEceRep] low 16 bits of conf * 2^31
+  unsigned* w_hi = w_lo + kConsWarps * nb * kEceRep;                              // [warps][nb][kEceRep] high 15 bits
+  unsigned* s_auroc = w_hi + kConsWarps * nb * kEceRep;  // [2*NB]
   float* units = reinterpret_cast<float*>(smem + v2_ring_offset(kConsWarps, nb, NB));
   {
     unsigned* w = s_cnt;
     const int words = 8 + 368;
     for (int i = threadIdx.x; i < words; i += kV2Threads) w[i] = 0u;
-    unsigned* w2 = reinterpret_cast<unsigned*>(w_cnt64);
-    const int words2 = kConsWarps * nb * 9 + 2 * NB;
+    unsigned* w2 = w_cnt;
+    const int words2 = kConsWarps * nb * (2 + 2 * kEceRep) + 2 * NB;
     for (int i = threadIdx.x; i < words2; i += kV2Threads) w2[i] = 0u;
     for (int i = threadIdx.x; i <= nb; i += kV2Threads) s_edges[i] = p.edges[i];
     if (threadIdx.x == 0) {
@@ -295,11 +298,11 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   const int div_mode = DIV >= 0 ? DIV : p.div_mode;
   unsigned n_correct = 0, n_bad = 0, n_ambig = 0;
   unsigned u = 0, ph = 0, since_flush = 0;
-  unsigned* my_cc = w_cc + warp * nb;
-  unsigned* my_lo = w_lo + warp * nb;
-  unsigned* my_hi = w_hi + warp * nb;
-  const uint32_t conf_sa = smem_u32(s_conf), auroc_sa = smem_u32(s_auroc), cc_sa = smem_u32(my_cc);
-  const uint32_t ece_stride = (uint32_t)(kConsWarps * nb * 4);  // my_cc -> my_lo -> my_hi
+  unsigned* my_lo = w_lo + warp * nb * kEceRep;
+  unsigned* my_hi = w_hi + warp * nb * kEceRep;
+  const uint32_t conf_sa = smem_u32(s_conf), auroc_sa = smem_u32(s_auroc);
+  const uint32_t cnt_sa = smem_u32(w_cnt + warp * nb), cor_sa = smem_u32(w_cor + warp * nb);
+  const uint32_t lo_sa = smem_u32(my_lo) + 4u * (lane & (kEceRep - 1)), hi_sa = smem_u32(my_hi) + 4u * (lane & (kEceRep - 1));
   const uint32_t sbase = smem_u32(smem);                                  // full[u] at sbase + 8u, empty[u] at + 8(kMaxUnits + u)
   const uint32_t my_unit0 = sbase + (uint32_t)v2_ring_offset(kConsWarps, nb, NB) + 4u * (uint32_t)t;
   // B * HW < 2^32 (score_v2_supported): all pixel and tile indices of the consumers are 32 bit
@@ -577,14 +580,18 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
 
     // ---- statistics
     if (have_labels) {
-      if (since_flush + 32u > kFlushPixels) {  // warp-uniform
+      if (since_flush + 32u > kFlushPixels) {  // warp-uniform, rare: move the 32-bit sums to the global bins
         __syncwarp();
         for (int i = lane; i < nb; i += 32) {
-          const unsigned cc = my_cc[i];
-          w_cnt64[warp * nb + i] += cc & 0xffffu;
-          w_cor64[warp * nb + i] += cc >> 16;
-          w_sum64[warp * nb + i] += ((u64)my_hi[i] << 16) + my_lo[i];
-          my_cc[i] = my_lo[i] = my_hi[i] = 0u;
+          u64 sum = 0;
+          for (int r = 0; r < kEceRep; ++r) {
+            sum += ((u64)my_hi[i * kEceRep + r] << 16) + my_lo[i * kEceRep + r];
+            my_hi[i * kEceRep + r] = my_lo[i * kEceRep + r] = 0u;
+          }
+          if (sum) {
+            atomicAdd(p.bins + p.lay.ece_conf_hi + i, sum >> 32);
+            atomicAdd(p.bins + p.lay.ece_conf_lo + i, sum & 0xffffffffull);
+          }
         }
         __syncwarp();
         since_flush = 0;
@@ -621,10 +628,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
             if (ckey >= 0) red_add(conf_sa + 4u * ckey, 32u);
             if (akey >= 0) red_add(auroc_sa + 4u * akey, 32u);
             if (bin >= 0) {
-              const uint32_t ba = cc_sa + 4u * bin;
-              red_add(ba, 32u | (correct ? (32u << 16) : 0u));
-              red_add(ba + ece_stride, lo);
-              red_add(ba + 2u * ece_stride, hi);
+              red_add(cnt_sa + 4u * bin, 32u);
+              if (correct) red_add(cor_sa + 4u * bin, 32u);
+              red_add(lo_sa + 4u * kEceRep * bin, lo);
+              red_add(hi_sa + 4u * kEceRep * bin, hi);
             }
           }
         }
@@ -632,17 +639,17 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         // the common case under ONE branch: five reductions, no reconvergence point between them
         red_add(conf_sa + 4u * ckey, 1u);
         if (ENS && NB > 0) red_add(auroc_sa + 4u * akey, 1u);
-        const uint32_t ba = cc_sa + 4u * bin;
-        red_add(ba, 1u | (correct ? 0x10000u : 0u));
-        red_add(ba + ece_stride, fx & 0xffffu);
-        red_add(ba + 2u * ece_stride, fx >> 16);
+        red_add(cnt_sa + 4u * bin, 1u);
+        red_add_if(correct ? 0 : -1, cor_sa + 4u * bin, 1u);
+        red_add(lo_sa + 4u * kEceRep * bin, fx & 0xffffu);
+        red_add(hi_sa + 4u * kEceRep * bin, fx >> 16);
       } else {
         red_add_if(ckey, conf_sa + 4u * ckey, 1u);
         red_add_if(akey, auroc_sa + 4u * akey, 1u);
-        const uint32_t ba = cc_sa + 4u * bin;
-        red_add_if(bin, ba, 1u | (correct ? 0x10000u : 0u));
-        red_add_if(bin, ba + ece_stride, fx & 0xffffu);
-        red_add_if(bin, ba + 2u * ece_stride, fx >> 16);
+        red_add_if(bin, cnt_sa + 4u * bin, 1u);
+        red_add_if(correct ? bin : -1, cor_sa + 4u * bin, 1u);
+        red_add_if(bin, lo_sa + 4u * kEceRep * bin, fx & 0xffffu);
+        red_add_if(bin, hi_sa + 4u * kEceRep * bin, fx >> 16);
       }
     }
     tin += step_tin;
@@ -682,10 +689,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   for (int i = t; i < nb; i += kCons) {
     u64 cnt = 0, cor = 0, sum = 0;
     for (int w = 0; w < kConsWarps; ++w) {
-      const unsigned cc = w_cc[w * nb + i];
-      cnt += w_cnt64[w * nb + i] + (cc & 0xffffu);
-      cor += w_cor64[w * nb + i] + (cc >> 16);
-      sum += w_sum64[w * nb + i] + ((u64)w_hi[w * nb + i] << 16) + w_lo[w * nb + i];
+      cnt += w_cnt[w * nb + i];
+      cor += w_cor[w * nb + i];
+      for (int r = 0; r < kEceRep; ++r)
+        sum += ((u64)w_hi[(w * nb + i) * kEceRep + r] << 16) + w_lo[(w * nb + i) * kEceRep + r];
     }
     part_ece += (unsigned)cnt;
     part_cor += (unsigned)cor;
