@@ -469,7 +469,11 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       sa = sa2.x + sa2.y;
       sb = sb2.x + sb2.y;
       const float tsa = ta2.x + ta2.y, tsb = tb2.x + tb2.y;
-      const float ra = rcp_approx(sa), rb = rcp_approx(sb);
+      // one reciprocal for both member sums: 1/Sa = Sb r, 1/Sb = Sa r with r = rcp(Sa Sb) (tying 1/Sz in as
+      // well was measured slower: it makes the log phase wait for the fused-logit phase)
+      const float sab = sa * sb;
+      const float rab = rcp_approx(sab);
+      const float ra = sb * rab, rb = sa * rab;
       // mean probabilities m_c = (e^a_c/Sa + e^b_c/Sb)/2 = ka * u_c with u_c = e^a_c + rho e^b_c
       const float kas = 0.5f * ra, kbs = 0.5f * rb;
       const float2 ka = splat(kas), rho = splat(sa * rb);
@@ -495,13 +499,14 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       }
       // entropies in bits: H2(p) = lg2 S' - (sum e'_c t_c)/S'; the reference's log(p + eps) adds
       // -C*eps nats (p >> eps)
-      const float lsa = lg2_approx(sa), lsb = lg2_approx(sb);
-      const float ha2 = lsa - tsa * ra, hb2 = lsb - tsb * rb;
+      // only lg2 Sa' + lg2 Sb' = lg2(Sa' Sb') enters the mutual information: one logarithm
+      const float lsab = lg2_approx(sab);
       const float ceps = (float)kC * kEps;
-      mi = kLn2 * (-kas * (hm2.x + hm2.y) - 0.5f * (ha2 + hb2)) + ceps;
+      mi = kLn2 * (-kas * (hm2.x + hm2.y) - 0.5f * (lsab - tsa * ra - tsb * rb)) + ceps;
       if (JS) {
         // sum_c m_c lg2 p_c = ka*Ta + kb*Xba - lg2 Sa' ; sum_c m_c lg2 q_c = kb*Tb + ka*Xab - lg2 Sb'
         const float xab = xab2.x + xab2.y, xba = xba2.x + xba2.y;
+        const float lsa = lg2_approx(sa), lsb = lg2_approx(sb);
         const float mlp = kas * tsa + kbs * xba - lsa;
         const float mlq = kbs * tsb + kas * xab - lsb;
         js = kLn2 * (mlm - 0.5f * (mlp + mlq));
@@ -611,11 +616,15 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         if (ENS && NB > 0) {
           // floor(mi * scale) clamped to [0, NB-1]; NaN -> 0 (fmaxf returns the non-NaN operand)
           const float qv = fminf(fmaxf(mi * p.auroc_scale, 0.f), p.auroc_top);
-          akey = (lab != marg ? 0 : NB) + (int)qv;
+          // floor of 0 <= qv < 2^23 without the conversion pipe: round-down add of 2^23, low mantissa bits
+          akey = (lab != marg ? 0 : NB) + (__float_as_int(__fadd_rd(qv, 8388608.f)) & 0x7fffff);
         }
       }
       if (!valid) bin = -1;
-      const unsigned fx = bin >= 0 ? __float2uint_rz(conf * 2147483648.f) : 0u;
+      // conf * 2^31 as an integer without the conversion pipe: 1/19 <= conf <= 1, so the product is >= 2^23 and
+      // integer valued: its 24-bit significand shifted left by (exponent - 23)
+      const unsigned cb = __float_as_uint(conf);
+      const unsigned fx = bin >= 0 ? (((cb & 0x7fffffu) | 0x800000u) << ((cb >> 23) - 119u)) : 0u;
       // one warp-uniformity test for all three histograms (piecewise-constant real data)
       const int key = (ckey + 1) | ((akey + 1) << 9) | ((bin + 1) << 23);
       int same;
