@@ -51,6 +51,13 @@ __device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// true for exactly one (the first active) lane of a converged warp: the pattern ptxas recognises to keep the
+// operands of the elected thread's instructions in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred = 0;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n @p mov.u32 %0, 1;\n}" : "+r"(pred));
+  return pred != 0;
+}
 // the same operations on 32-bit shared addresses (the hot loops keep one shared base register and add
 // immediates; converting a generic pointer costs an S2R + LEA every time)
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   const long long tpi = (HW + kTP - 1) / kTP;  // tiles per image
   const long long ntiles = p.B * tpi;
 
-  if (warp == kConsWarps) {
+  if (threadIdx.x >= kCons) {  // (threadIdx.x, not the opaque copy of %tid.x: the compiler must see a warp-uniform branch)
     // ------------------------------------------------------------------ producer warp
     unsigned u = 0, ph = 0;
     long long img = blockIdx.x / tpi, tin = blockIdx.x - img * tpi;
@@ -268,12 +275,18 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
 #pragma unroll
       for (int m = 0; m < (ENS ? 2 : 1); ++m) {
         mbar_wait(empty + u, ph ^ 1u);
-        if (lane == 0) mbar_expect_tx(full + u, kC * npx * 4u);
-        __syncwarp();
-        if (lane < kC) {
-          const float* src = (m == 0 ? p.a : p.b) + (img * kC + lane) * HW + p0;
-          bulk_load(units + (size_t)u * kUnitFloats + lane * kTP, src, npx * 4u, full + u);
+        // ONE thread issues the 19 copies of the unit from warp-uniform operands: the copy instruction takes
+        // uniform registers, and per-lane addresses would make the compiler broadcast every lane's operands one
+        // after the other (ELECT / 4 x R2UR / UBLKCP per copy: ~190 instructions per unit, which kept this warp
+        // busy 70 % of the time)
+        if (elect_one()) {
+          mbar_expect_tx(full + u, kC * npx * 4u);
+          const float* src = (m == 0 ? p.a : p.b) + img * kC * HW + p0;
+          float* dst = units + (size_t)u * kUnitFloats;
+#pragma unroll
+          for (int c = 0; c < kC; ++c) bulk_load(dst + c * kTP, src + c * HW, npx * 4u, full + u);
         }
+        __syncwarp();
         if (++u == (unsigned)NU) {
           u = 0;
           ph ^= 1u;

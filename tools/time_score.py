@@ -11,18 +11,20 @@ lb = torch.randn(B, c, h, w, device=dev)
 tgt = torch.randint(0, c, (B, h, w), device=dev).to(torch.uint8)
 px = B * h * w
 
-def timeit(name, fn, bytes_per_px, n=5):
+def timeit(name, fn, bytes_per_px, n=20):
+    """median (and min) of n individually timed launches"""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    for _ in range(n):
+    ev = [(torch.cuda.Event(True), torch.cuda.Event(True)) for _ in range(n)]
+    for e0, e1 in ev:
+        e0.record()
         fn()
-    e1.record()
+        e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    print(f"{name:34s} {ms:8.3f} ms  {px/ms/1e3:9.1f} Mpx/s  {px*bytes_per_px/ms/1e6:8.1f} GB/s", flush=True)
+    t = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+    ms, mn = t[len(t) // 2], t[0]
+    print(f"{name:34s} {ms:8.3f} ms (min {mn:6.3f})  {px/ms/1e3:9.1f} Mpx/s  {px*bytes_per_px/ms/1e6:8.1f} GB/s", flush=True)
 
 bins1 = ops.new_bins(c, 15, 0)
 bins2 = ops.new_bins(c, 15, 4096)
