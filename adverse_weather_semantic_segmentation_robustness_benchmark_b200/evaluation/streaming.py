@@ -76,6 +76,17 @@ class StreamingEvaluator:
         ops.corrupt_score(images, params, field, items, out, workspace, logits_a,
                           logits_b if self.ensemble else None, labels, cfg, row)
 
+    def canonical_bins(self) -> torch.Tensor:
+        """The bins with every confidence sum in canonical form.  A sum is stored as hi * 2^32 + lo where both
+        words are plain accumulators (each launch / CTA / rank adds its own split), so two buffers holding the
+        same sums can differ word by word; here the carry of `lo` is folded into `hi`."""
+        out = self.bins.clone()
+        hi = slice(int(self.layout.ece_conf_hi), int(self.layout.ece_conf_hi) + self.ece_bins)
+        lo = slice(int(self.layout.ece_conf_lo), int(self.layout.ece_conf_lo) + self.ece_bins)
+        out[:, hi] += out[:, lo] >> 32
+        out[:, lo] &= 0xFFFFFFFF
+        return out
+
     def all_reduce(self, group=None) -> None:
         """Merge the bins of all ranks (NCCL over NVLink on GPUs; any backend that sums int64)."""
         import torch.distributed as dist

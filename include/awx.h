@@ -103,7 +103,8 @@ typedef struct AwxScoreMaps {
  *   confusion  [C*C]      rows = target, cols = prediction
  *   ece_count  [nb]       pixels with edges[b] < conf <= edges[b+1]
  *   ece_correct[nb]       of those, pred == target
- *   ece_conf_hi[nb], ece_conf_lo[nb]   sum of conf in 2^-31 fixed point = hi*2^32 + lo
+ *   ece_conf_hi[nb], ece_conf_lo[nb]   sum of conf in 2^-31 fixed point = hi*2^32 + lo; both words are plain
+ *                          accumulators (lo may exceed 2^32), so equal sums need not be equal word by word
  *   auroc_pos  [NB], auroc_neg[NB]     MI histogram of wrong / right ensemble pixels
  *   counters   [8]        AWX_CNT_*                                                   */
 typedef struct AwxBinsLayout {

@@ -150,3 +150,21 @@ def test_corrupt_score_single_call_equals_two_calls():
         ev2.update("x", la, lb, lab)
         assert torch.equal(out1, out2) and torch.equal(ev1.bins, ev2.bins)
         assert int(ev1.bins.sum()) > 0
+
+
+def test_chunked_updates_equal_one_update():
+    """Scoring a batch in chunks gives the same bins as one launch: every count identical, the confidence sums
+    identical in canonical form (hi/lo words are plain accumulators and split differently per launch)."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import StreamingEvaluator
+    gen = torch.Generator().manual_seed(8)
+    b, h, w = 6, 96, 160
+    la = (torch.randn(b, C, h, w, generator=gen) * 2).cuda()
+    lb = (torch.randn(b, C, h, w, generator=gen) * 2).cuda()
+    lab = torch.randint(0, C, (b, h, w), generator=gen).to(torch.uint8).cuda()
+    kw = dict(auroc_bins=4096, ensemble_weights=(0.3, 0.9), temperature=1.7)
+    one, many = StreamingEvaluator(C, ("x",), **kw), StreamingEvaluator(C, ("x",), **kw)
+    one.update("x", la, lb, lab)
+    for k in range(0, b, 2):
+        many.update("x", la[k:k + 2], lb[k:k + 2], lab[k:k + 2])
+    assert torch.equal(one.canonical_bins(), many.canonical_bins())
+    assert one.finalize() == many.finalize()
