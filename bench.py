@@ -369,9 +369,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                          "ms_per_launch": score_ms,
                          "whole_step_GBps": step_bytes / (ms_step * 1e-3) / 1e9},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "parity": {"ece_ambiguous_pixels": int(sum(v.get("ece_ambiguous_pixels", 0)
-                                                       for v in wl.ev.per_condition().values())),
-                       "overall_miou": results.get("overall_miou")},
+            "parity": parity_object(wl, results, world),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -445,6 +443,27 @@ def run_sweep(args, rank, world, local_rank):
             "bins_checksum": int(wl.ev.bins.sum().item())}), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_object(wl, results, world):
+    """Parity gates reported with the benchmark: the step's own counters, a small probe of the
+    hot path against the CPU oracle (N = 1 only: the oracle is the checker here, never the thing measured), and
+    the versions of the libraries whose arithmetic the oracle calls."""
+    out = {"ece_ambiguous_pixels": int(sum(v.get("ece_ambiguous_pixels", 0) for v in wl.ev.per_condition().values())),
+           "overall_miou": results.get("overall_miou")}
+    if world == 1:
+        try:
+            import __graft_entry__ as entry
+            out["oracle_probe"] = entry.parity_probe()
+        except Exception as exc:  # a failed gate must be visible in the line, not kill the measurement
+            out["oracle_probe"] = {"failed": repr(exc)[:300]}
+    try:
+        import cv2, numpy, scipy, sklearn, torch
+        out["versions"] = {"numpy": numpy.__version__, "cv2": cv2.__version__, "scipy": scipy.__version__,
+                           "torch": torch.__version__, "sklearn": sklearn.__version__}
+    except Exception:
+        pass
+    return out
 
 
 def run_e2e(args, wl, device, world, barrier, max_over_ranks, px_step):
