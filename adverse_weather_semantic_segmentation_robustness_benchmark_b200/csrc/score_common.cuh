@@ -151,7 +151,8 @@ __device__ __forceinline__ void score_pixel(float (&a)[CS > 0 ? CS : AWX_MAX_CLA
   int bin = ece_bin(conf, s_edges, p.nb);
   o.ambig = 0;
   if (bin >= 0) {
-    const float tol = conf * 1.9e-6f;  // 16 ulp
+    // 16 ulp, plus the reference's rounding of z = v/T when it divides before the softmax (see score_v2.cu)
+    const float tol = conf * (p.div_mode == 1 ? fmaf(fabsf(vmax / T), 1.5e-7f, 2.4e-6f) : 1.9e-6f);
     const bool near_lo = bin > 0 && (conf - s_edges[bin]) <= tol;
     const bool near_hi = bin < p.nb - 1 && (s_edges[bin + 1] - conf) <= tol;
     if (near_lo || near_hi) {

@@ -537,6 +537,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       const float r0 = rcp_approx(sz);
       const float r = fmaf(r0, fmaf(-sz, r0, 1.f), r0);  // one Newton step: <= 1 ulp
       conf = fminf(fmaf(r, zdelta, r), 1.f);
+      // relative half-width of the "near an edge" band: 16 ulp for this kernel's own error, plus -- when the
+      // reference divides the logits by T in fp32 before its softmax (div_mode 1: this kernel keeps the exact
+      // quotient in the exponent instead) -- the reference's own rounding of z = v/T, ~ulp(zmax) relative
+      const float band = div_mode == 1 ? fmaf(fabsf(vmax * p.rT), 1.5e-7f, 2.4e-6f) : 2.4e-6f;
       bool near;
       if (FAST != 0) {
         // edges are linspace(0,1,nb+1) (checked by the host): bin = ceil(conf*nb) - 1 unless conf is
@@ -546,12 +550,12 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         const int j = __float_as_int(tt) - 0x4b400000;
         const float d = s - (tt - 12582912.f);
         bin = min(j - (d < 0.f ? 1 : 0), nb - 1);
-        near = fabsf(d) <= s * 2.4e-6f && j < nb;
+        near = fabsf(d) <= s * band && j < nb;
       } else {
         bin = ece_bin_fast(conf, s_edges, nb);
         near = false;
         if (bin >= 0) {
-          const float tol = conf * 1.9e-6f;  // 16 ulp
+          const float tol = conf * band;
           near = (bin > 0 && (conf - s_edges[bin]) <= tol) || (bin < nb - 1 && (s_edges[bin + 1] - conf) <= tol);
         }
       }
