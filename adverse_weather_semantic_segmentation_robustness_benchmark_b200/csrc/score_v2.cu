@@ -36,11 +36,12 @@ struct Geo {
   static constexpr int kUnitFloats = kC * kTP;
   static constexpr int kUnitBytes = kUnitFloats * 4;
 };
-constexpr int kMaxUnits = 5;
+constexpr int kMaxUnits = 4;                    // ring depth: 3, 4 and 5 units measure the same; the shared memory is
+                                                // better spent on conflict-free statistics
 constexpr int kFastEceBins = 15, kFastAurocBins = 4096;  // the streaming evaluator's configuration
 constexpr int kSingleWarps = 19;                // consumer warps of the bins-only single-member kernels
 constexpr unsigned kFlushPixels = 60000;        // per-warp confidence sums are flushed before 2^16 pixels
-constexpr int kEceRep = 4;                      // replicas (lane & 3) of the per-warp confidence-sum words
+constexpr int kEceRep = 16;                     // replicas (lane & 15) of the per-warp confidence-sum words
 
 typedef unsigned long long u64;
 
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   // per-warp ECE words.  Counts take the value 1 (the hardware aggregates lanes hitting the same word:
   // ATOMS.POPC.INC, ~3 wavefronts); the confidence sums carry per-lane values, and a shared-memory atomic add
   // whose lanes collide on one address is serialised lane by lane (measured: 28 wavefronts per instruction with
-  // ~10 lanes per bin), so every (warp, bin) sum has kEceRep replicas selected by lane & 3.
+  // ~10 lanes per bin), so every (warp, bin) sum has kEceRep replicas selected by lane & 15.
   unsigned* w_cnt = reinterpret_cast<unsigned*>(s_edges + AWX_MAX_ECE_BINS + 4);  // [warps][nb]
   unsigned* w_cor = w_cnt + kConsWarps * nb;                                      // [warps][nb]
   unsigned* w_lo = w_cor + kConsWarps * nb;                                       // [warps][nb][kEceRep] low 16 bits of conf * 2^31
@@ -766,6 +767,10 @@ int launch_v2(const ScoreParams& p, cudaStream_t stream) {
   const size_t fixed = v2_ring_offset(CW, p.nb, p.auroc_bins);
   int nu = (int)(((size_t)max_smem - fixed) / G::kUnitBytes);
   if (nu > kMaxUnits) nu = kMaxUnits;
+  if (const char* e = getenv("AWX_V2_UNITS")) {  // dev knob: ring depth sensitivity
+    const int want = atoi(e);
+    if (want >= 2 && want < nu) nu = want;
+  }
   AWX_REQUIRE(nu >= 2, AWX_E_UNSUPPORTED, "awx_score v2: histograms leave no room for the TMA ring");
   const size_t smem = (size_t)nu * G::kUnitBytes + fixed;
   AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
