@@ -73,6 +73,9 @@ _SIGNATURES = {
     "awx_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                             C.POINTER(ScoreConfig), C.c_void_p, C.POINTER(ScoreMaps), C.c_void_p]),
     "awx_member_variance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p]),
+    "awx_members_n": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
+                                C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
     "awx_confusion": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p]),
     "awx_corrupt_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),

@@ -122,20 +122,20 @@ class EnsembleDisagreementMetrics:
     def _two_members(predictions_list: List[torch.Tensor]):
         if len(predictions_list) < 2:
             raise ValueError("Need at least 2 predictions for disagreement computation")
-        if len(predictions_list) > 2:
-            raise NotImplementedError(
-                "libawx scores two-member ensembles (the reference's SegFormer + DeepLabV3+ pair); "
-                f"got {len(predictions_list)} members")
         return _as_logits(predictions_list[0]), _as_logits(predictions_list[1])
 
     def compute_disagreement_map(self, predictions_list: List[torch.Tensor]) -> torch.Tensor:
         """metrics.py:336-369: H(mean p) - mean_k H(p_k) with the reference's log(p + 1e-8); [B,H,W]."""
         a, b = self._two_members(predictions_list)
+        if len(predictions_list) > 2:  # the general list form (awx_members_n); two members ride along in awx_score
+            return ops.members_n(predictions_list, want_mi=True)["mi"]
         return ops.score(a, b, strategy=_lib.FUSE_MEAN, want_mi=True)["mi"]
 
     def compute_variance_map(self, predictions_list: List[torch.Tensor]) -> torch.Tensor:
         """metrics.py:371-391: unbiased variance over members of the class probabilities; [B,C,H,W]."""
         a, b = self._two_members(predictions_list)
+        if len(predictions_list) > 2:
+            return ops.members_n(predictions_list, want_var=True)["var"]
         return ops.member_variance(a, b)
 
     def compute_disagreement_auroc(self, predictions_list: List[torch.Tensor], targets: torch.Tensor,
@@ -146,6 +146,10 @@ class EnsembleDisagreementMetrics:
         Mann-Whitney statistic of the binned score; its distance from sklearn's value on the
         unbinned score is at most ``bound`` (returned with ``return_bound=True``)."""
         a, b = self._two_members(predictions_list)
+        if len(predictions_list) > 2:
+            out = ops.members_n(predictions_list, targets, auroc_bins=num_bins)
+            value, bound = finalize.auroc_from_histogram(out["pos"].cpu().numpy(), out["neg"].cpu().numpy())
+            return (value, bound) if return_bound else value
         out = ops.score(a, b, targets, strategy=_lib.FUSE_MEAN, auroc_bins=num_bins)
         bins = ops.read_bins(out["bins"], a.shape[1], 15, num_bins)
         value, bound = finalize.auroc_from_histogram(bins.auroc_pos, bins.auroc_neg)

@@ -214,6 +214,42 @@ def member_variance(logits_a: torch.Tensor, logits_b: torch.Tensor) -> torch.Ten
     return out
 
 
+def members_n(members, labels: Optional[torch.Tensor] = None, *, ignore_index: int = 255, auroc_bins: int = 0,
+              auroc_hi: Optional[float] = None, want_mi: bool = False, want_var: bool = False) -> dict:
+    """awx_members_n: disagreement of a list of N >= 2 members ([B,C,H,W] fp32 each).  Returns a dict with the
+    requested maps (``mi`` [B,H,W], ``var`` [B,C,H,W]) and, with labels, ``pos`` / ``neg`` (int64 [auroc_bins]) and
+    ``counters`` (int64 [8]).  The MI of N members lies in [0, ln N): that is the default histogram range."""
+    lib = _lib.load()
+    ms = [to_device(m, torch.float32) for m in members]
+    if len(ms) < 2:
+        raise ValueError("Need at least 2 predictions for disagreement computation")
+    if any(m.shape != ms[0].shape or m.dim() != 4 for m in ms):
+        raise ValueError("members must be [B,C,H,W] tensors of equal shape")
+    bsz, ncls, h, w = ms[0].shape
+    dev = ms[0].device
+    lab = None
+    if labels is not None:
+        lab = normalise_labels(labels)
+        if lab.numel() != bsz * h * w:
+            raise ValueError(f"labels have {lab.numel()} elements, expected {bsz * h * w}")
+    out = {}
+    if want_mi:
+        out["mi"] = torch.empty((bsz, h, w), dtype=torch.float32, device=dev)
+    if want_var:
+        out["var"] = torch.empty_like(ms[0])
+    if lab is not None:
+        out["pos"] = torch.zeros(max(auroc_bins, 1), dtype=torch.int64, device=dev)
+        out["neg"] = torch.zeros(max(auroc_bins, 1), dtype=torch.int64, device=dev)
+        out["counters"] = torch.zeros(8, dtype=torch.int64, device=dev)
+    ptrs = (C.c_void_p * len(ms))(*[m.data_ptr() for m in ms])
+    hi = float(auroc_hi) if auroc_hi is not None else math.log(len(ms))
+    rc = lib.awx_members_n(ptrs, len(ms), _ptr(lab), _lib.LABEL_I64 if lab is None else label_code(lab), bsz, ncls, h * w,
+                           ignore_index, auroc_bins if lab is not None else 0, hi, _ptr(out.get("pos")), _ptr(out.get("neg")),
+                           _ptr(out.get("counters")), _ptr(out.get("mi")), _ptr(out.get("var")), _stream())
+    _lib.check(rc, "awx_members_n")
+    return out
+
+
 def confusion(pred: torch.Tensor, labels: torch.Tensor, num_classes: int, ignore_index: int = 255):
     """(confusion int64 [C,C] device tensor, counters int64 [8] device tensor) from prediction maps."""
     lib = _lib.load()

@@ -146,6 +146,16 @@ int awx_confusion(const void* pred, int32_t pred_dtype, const void* labels, int3
 int awx_member_variance(const float* logits_a, const float* logits_b, float* out,
                         int64_t batch, int32_t num_classes, int64_t pixels_per_image, void* stream);
 
+/* EnsembleDisagreementMetrics for a LIST of N >= 2 members (evaluation/metrics.py:336-438; two members run inside
+ * awx_score): mi_out [B,HW] = H(mean_k p_k) - mean_k H(p_k); var_out [B,C,HW] = unbiased variance over members;
+ * with labels: auroc_pos / auroc_neg int64 [auroc_bins] histograms of mi over [0, auroc_hi) for pixels whose
+ * argmax(mean p) != / == label, counters int64 [8] (AWX_CNT_VALID, AWX_CNT_ENS_WRONG, AWX_CNT_PIXELS); all accumulate.
+ * members: HOST array of n_members device pointers to fp32 [B,C,HW]; every output pointer may be NULL. */
+int awx_members_n(const float* const* members /*HOST*/, int32_t n_members, const void* labels, int32_t label_dtype,
+                  int64_t batch, int32_t num_classes, int64_t pixels_per_image, int32_t ignore_index,
+                  int32_t auroc_bins, float auroc_hi, int64_t* auroc_pos, int64_t* auroc_neg, int64_t* counters,
+                  float* mi_out, float* var_out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Weather corruption (WeatherDegradationTransforms, data/preprocessing.py:61-248).
  * Stochastic parameters are drawn on the host with the reference's RNG and passed in.

@@ -230,6 +230,21 @@ def prep_cases():
         tg = targets.view(-1)[targets.view(-1) != 255]
         out[f"{tag}_nll"] = np.array([torch.nn.functional.cross_entropy(rows / t, tg).item()
                                       for t in torch.linspace(0.1, 10.0, 100)], dtype=np.float64)
+    # EnsembleDisagreementMetrics on LISTS of three and four members (the list form of metrics.py:336-438)
+    ens = met.EnsembleDisagreementMetrics()
+    torch.manual_seed(77)
+    for tag, (n, b, c, h, w, ign) in {"m3": (3, 2, 19, 24, 32, 0.03), "m4": (4, 1, 5, 16, 20, 0.0)}.items():
+        base = torch.randn(b, c, h, w) * 2
+        members = [base * 0.5 + torch.randn(b, c, h, w) * (1.0 + 0.5 * k) for k in range(n)]
+        targets = torch.randint(0, c, (b, h, w))
+        if ign > 0:
+            targets[torch.rand(b, h, w) < ign] = 255
+        for k, m in enumerate(members):
+            out[f"{tag}_member{k}"] = m.numpy()
+        out[f"{tag}_targets"] = targets.numpy()
+        out[f"{tag}_mi"] = ens.compute_disagreement_map(members).numpy()
+        out[f"{tag}_var"] = ens.compute_variance_map(members).numpy()
+        out[f"{tag}_auroc"] = np.float64(ens.compute_disagreement_auroc(members, targets))
     np.savez_compressed(os.path.join(HERE, "prep.npz"), **out)
 
 

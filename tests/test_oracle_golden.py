@@ -266,3 +266,14 @@ def test_normalize_chw_restatement():
     assert got.dtype == np.float32 and got.shape == (3, 20, 28)
     want = (img.astype(np.float64) / 255.0 - np.array(op.IMAGENET_MEAN)) / np.array(op.IMAGENET_STD)
     np.testing.assert_allclose(got, want.transpose(2, 0, 1), rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("tag,n", [("m3", 3), ("m4", 4)])
+def test_member_lists_match_reference(golden, tag, n):
+    g = golden("prep")
+    exact = _same_versions(g)
+    members = [torch.from_numpy(g[f"{tag}_member{k}"]) for k in range(n)]
+    targets = torch.from_numpy(g[f"{tag}_targets"])
+    _eq(om.mi_map(members).numpy(), g[f"{tag}_mi"], exact, atol=2e-6, rtol=1e-5)
+    _eq(om.variance_map(members).numpy(), g[f"{tag}_var"], exact, atol=1e-7, rtol=1e-5)
+    assert om.disagreement_auroc(members, targets) == float(g[f"{tag}_auroc"])

@@ -303,3 +303,23 @@ def test_full_size_bins_only_kernels_match_generic(pkg, mode, temp, ldt):
         # the MI value of a pixel is the same arithmetic in both kernels; a handful of pixels may sit on a
         # histogram edge after the different instruction scheduling -- none are expected
         assert np.abs(fast.auroc_pos - slow.auroc_pos).sum() + np.abs(fast.auroc_neg - slow.auroc_neg).sum() <= 4
+
+
+@pytest.mark.parametrize("tag,n", [("m3", 3), ("m4", 4)])
+def test_member_lists_golden(pkg, golden, tag, n):
+    """EnsembleDisagreementMetrics on lists of more than two members (awx_members_n) against the reference."""
+    p, ops, _lib = pkg
+    g = golden("prep")
+    members = [torch.from_numpy(g[f"{tag}_member{k}"]) for k in range(n)]
+    targets = torch.from_numpy(g[f"{tag}_targets"])
+    ens = p.EnsembleDisagreementMetrics()
+    _close(ens.compute_disagreement_map(members).cpu().numpy(), g[f"{tag}_mi"])
+    _close(ens.compute_variance_map(members).cpu().numpy(), g[f"{tag}_var"], rtol=1e-5, atol=1e-7)
+    val, bound = ens.compute_disagreement_auroc(members, targets, return_bound=True)
+    assert abs(val - float(g[f"{tag}_auroc"])) <= bound + 1e-6 and bound < 2e-3
+    # two members through the list kernel == the fused kernel's maps (same formulas, different code)
+    two = ops.members_n(members[:2], want_mi=True, want_var=True)
+    _close(two["mi"].cpu().numpy(), ops.score(members[0], members[1], strategy=_lib.FUSE_MEAN, want_mi=True)["mi"].cpu().numpy())
+    _close(two["var"].cpu().numpy(), ops.member_variance(members[0], members[1]).cpu().numpy(), rtol=1e-5, atol=1e-7)
+    with pytest.raises(ValueError, match="at least 2"):
+        ens.compute_disagreement_map(members[:1])
