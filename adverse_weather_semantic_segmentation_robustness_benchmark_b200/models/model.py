@@ -187,15 +187,7 @@ class FogDensityAwareLoss(nn.Module):
         return {"total_loss": total, "segmentation_loss": seg, "depth_loss": depth_loss}
 
     def _estimate_fog_density_from_depth(self, depth: torch.Tensor) -> torch.Tensor:
-        """model.py:644-677.  Host-side glue in torch ops (a [B,H,W] map, 4 B/px, three global
-        scalars); kept differentiable so that path B trains the depth head as the reference does."""
-        depth = ops.to_device(depth, torch.float32) if not depth.is_cuda else depth
-        unit = (depth - depth.min()) / (depth.max() - depth.min() + 1e-8)
-        density = unit * 0.7
-        gx = torch.abs(depth[:, :, 1:] - depth[:, :, :-1])
-        gy = torch.abs(depth[:, 1:, :] - depth[:, :-1, :])
-        gx = F.pad(gx, (0, 1, 0, 0), mode="replicate")
-        gy = F.pad(gy, (0, 0, 0, 1), mode="replicate")
-        mag = torch.sqrt(gx ** 2 + gy ** 2 + 1e-8)
-        density = density - (mag > mag.mean()) * 0.3
-        return torch.clamp(density, 0, 1)
+        """model.py:644-677: density from the predicted depth (global min / max, mean gradient magnitude), forward
+        and gradient in libawx (awx_depth_density_fwd / _bwd) so that path B trains the depth head as the
+        reference does."""
+        return ops_loss.depth_density(depth)

@@ -96,6 +96,40 @@ class _FogLossFn(torch.autograd.Function):
         return gl, gd, gf, None, None, None, None
 
 
+class _DepthDensityFn(torch.autograd.Function):
+    """fog density estimated from a predicted depth map (model.py:644-677): awx_depth_density_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, depth):
+        lib = _lib.load()
+        d = ops.to_device(depth.detach(), torch.float32)
+        if d.dim() != 3:
+            raise ValueError(f"depth must be [B,H,W], got {tuple(d.shape)}")
+        b, h, w = d.shape
+        out = torch.empty_like(d)
+        ws = torch.empty(int(lib.awx_depth_density_workspace_bytes()), dtype=torch.uint8, device=d.device)
+        _lib.check(lib.awx_depth_density_fwd(_ptr(d), _ptr(out), b, h, w, _ptr(ws), _stream()), "awx_depth_density_fwd")
+        ctx.save_for_backward(d)
+        ctx.src = (depth.device, depth.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (d,) = ctx.saved_tensors
+        b, h, w = d.shape
+        gg = ops.to_device(g, torch.float32)
+        gd = torch.empty_like(d)
+        ws = torch.empty(int(lib.awx_depth_density_workspace_bytes()), dtype=torch.uint8, device=d.device)
+        _lib.check(lib.awx_depth_density_bwd(_ptr(d), _ptr(gg), _ptr(gd), b, h, w, _ptr(ws), _stream()), "awx_depth_density_bwd")
+        return gd.to(ctx.src[1]).to(ctx.src[0])
+
+
+def depth_density(depth: torch.Tensor) -> torch.Tensor:
+    """Differentiable fog density from a [B,H,W] depth map; the result lives on the CUDA device."""
+    return _DepthDensityFn.apply(depth)
+
+
 def fog_loss_terms(logits, depth_pred, labels, fog_density, depth_tgt, sens: float, focal: bool):
     return _FogLossFn.apply(logits, depth_pred, fog_density, labels, depth_tgt, sens, focal)
 

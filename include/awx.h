@@ -238,6 +238,17 @@ int awx_fogloss(const float* logits, const void* labels, int32_t label_dtype,
                 double* sums, float* dlogits, float* ddepth, float* dfog /*nullable*/,
                 int64_t* bad_labels, void* workspace, void* stream);
 
+/* FogDensityAwareLoss._estimate_fog_density_from_depth (models/model.py:644-677) and its gradient:
+ * density = clamp(0.7 * (d - min d)/(max d - min d + 1e-8) - 0.3 * [|grad d| > mean |grad d|], 0, 1), min / max /
+ * mean over the whole [B,H,W] tensor.  bwd: grad_depth = d(sum grad_density * density)/d depth as autograd
+ * derives it (min / max terms spread evenly over the attaining elements).  workspace:
+ * awx_depth_density_workspace_bytes() bytes (need not persist between the two calls). */
+size_t awx_depth_density_workspace_bytes(void);
+int awx_depth_density_fwd(const float* depth, float* density, int64_t batch, int32_t height, int32_t width,
+                          void* workspace, void* stream);
+int awx_depth_density_bwd(const float* depth, const float* grad_density, float* grad_depth, int64_t batch,
+                          int32_t height, int32_t width, void* workspace, void* stream);
+
 /* x[i] *= *scale (device scalar) -- backward of a mean-reduced loss with grad_output != 1. */
 int awx_scale_inplace(float* x, int64_t n, const float* scale, void* stream);
 

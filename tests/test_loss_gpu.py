@@ -173,3 +173,32 @@ def test_ensemble_training_gradients(pkg):
     _close(got[0], want[0], 1e-5, 0)
     for gg, ww in zip(got[1:], want[1:]):
         _close(gg.cpu().numpy(), ww.numpy(), 2e-4, 1e-8)
+
+
+def test_depth_density_forward_backward(pkg, golden):
+    """_estimate_fog_density_from_depth in libawx: forward against the reference's golden output, gradient
+    against autograd of the oracle's restatement (the indicator edge mask carries no gradient; min / max do)."""
+    from oracle import loss as ol
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops_loss
+    g = golden("loss")
+    depth = torch.from_numpy(g["depth"]).squeeze(1)
+    got = pkg.FogDensityAwareLoss()._estimate_fog_density_from_depth(depth)
+    _close(got.cpu().numpy(), g["fd_from_depth"], 1e-6, 1e-7)
+    gen = torch.Generator().manual_seed(3)
+    for shape in ((2, 24, 40), (1, 2, 2), (3, 17, 33)):
+        d = (torch.rand(*shape, generator=gen) * 40).requires_grad_(True)
+        up = torch.randn(*shape, generator=gen)
+        ref = ol.fog_density_from_depth(d)
+        (ref * up).sum().backward()
+        dd = d.detach().clone().cuda().requires_grad_(True)
+        out = ops_loss.depth_density(dd)
+        (out * up.cuda()).sum().backward()
+        _close(out.detach().cpu().numpy(), ref.detach().numpy(), 1e-6, 1e-7)
+        _close(dd.grad.cpu().numpy(), d.grad.numpy(), 2e-5, 1e-7)
+    # ties at the extrema share the min / max gradient evenly, as torch's full-reduction backward does
+    d = torch.tensor([[[0.0, 5.0, 5.0], [0.0, 2.0, 3.0], [1.0, 4.0, 5.0]]], requires_grad=True)
+    up = torch.arange(9.0).reshape(1, 3, 3) + 1.0
+    (ol.fog_density_from_depth(d) * up).sum().backward()
+    dd = d.detach().clone().cuda().requires_grad_(True)
+    (ops_loss.depth_density(dd) * up.cuda()).sum().backward()
+    _close(dd.grad.cpu().numpy(), d.grad.numpy(), 2e-5, 1e-7)
