@@ -93,6 +93,9 @@ _SIGNATURES = {
                               C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "awx_fogloss_workspace_bytes": (C.c_size_t, []),
+    "awx_fuse_backward_workspace_bytes": (C.c_size_t, []),
+    "awx_fuse_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
+                                    C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "awx_depth_density_workspace_bytes": (C.c_size_t, []),
     "awx_depth_density_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "awx_depth_density_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,

@@ -78,13 +78,12 @@ class EnsembleModel(nn.Module):
 
     def fuse_depth(self, d1: torch.Tensor, d2: torch.Tensor) -> torch.Tensor:
         """model.py:471-478: weighted for weighted_average, plain mean otherwise; no temperature."""
-        if torch.is_grad_enabled() and (d1.requires_grad or d2.requires_grad):
-            if self.ensemble_strategy == "weighted_average":
-                w = F.softmax(self.ensemble_weights, dim=0)
-                return w[0] * d1 + w[1] * d2
-            return (d1 + d2) / 2
+        strategy = "weighted_average" if self.ensemble_strategy == "weighted_average" else "mean"
+        if torch.is_grad_enabled() and (d1.requires_grad or d2.requires_grad
+                                        or self.ensemble_weights.requires_grad and self.training):
+            return _FuseFn.apply(d1, d2, self.ensemble_weights, None, strategy)
         w0, w1, _ = self._fusion_scalars()
-        code = _lib.FUSE_WEIGHTED if self.ensemble_strategy == "weighted_average" else _lib.FUSE_MEAN
+        code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
         return ops.score(d1, d2, strategy=code, w0=w0, w1=w1, temperature=None, want_fused=True)["fused"]
 
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -112,47 +111,42 @@ class EnsembleModel(nn.Module):
 
 
 class _FuseFn(torch.autograd.Function):
-    """Differentiable fusion for training: forward through awx_score; backward is the closed form
-    of d(w0*a + w1*b)/T (weights go through their softmax), evaluated with torch reductions since
-    it is two scaled copies of the incoming gradient plus three dot products."""
+    """Differentiable fusion for training: forward through awx_score, backward through awx_fuse_backward (the two
+    scaled copies of the incoming gradient and the three dot products in one pass); only the 2-element softmax
+    Jacobian of the raw weights and the temperature's scalar are formed from those sums afterwards."""
 
     @staticmethod
     def forward(ctx, a, b, raw_w, temperature, strategy):
-        w = F.softmax(raw_w.detach().float(), dim=0)
+        w = F.softmax(raw_w.detach().float().cpu(), dim=0)
         w0, w1 = float(w[0]), float(w[1])
         temp = None if temperature is None else float(temperature.detach().float().reshape(-1)[0])
         code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
-        out = ops.score(a, b, strategy=code, w0=w0, w1=w1, temperature=temp, want_fused=True,
-                        want_conf=False)
-        fused = out["fused"]
-        ctx.save_for_backward(a, b, raw_w, temperature if temperature is not None else torch.ones(1), fused)
-        ctx.has_temp = temperature is not None
-        ctx.strategy = strategy
+        fused = ops.score(a, b, strategy=code, w0=w0, w1=w1, temperature=temp, want_fused=True)["fused"]
+        ctx.save_for_backward(a, b)
+        ctx.meta = (w0, w1, temp, code, raw_w, temperature)
         return fused
 
     @staticmethod
     def backward(ctx, g):
-        a, b, raw_w, temperature, fused = ctx.saved_tensors
-        dev = g.device
-        t = temperature.to(dev).float().reshape(-1)[0] if ctx.has_temp else torch.ones((), device=dev)
-        gs = g / t
-        ga = gb = gw = gt = None
-        if ctx.strategy == "weighted_average":
-            w = F.softmax(raw_w.to(dev).float(), dim=0)
-            ga, gb = gs * w[0], gs * w[1]
-            dots = torch.stack([(gs * a.to(dev)).sum(), (gs * b.to(dev)).sum()])
-            # softmax Jacobian: dL/draw_i = w_i * (dots_i - sum_j w_j dots_j)
-            gw = (w * (dots - (w * dots).sum())).to(raw_w.dtype).to(raw_w.device)
-        elif ctx.strategy == "max_confidence":
-            ca = F.softmax(a.to(dev), dim=1).max(dim=1)[0]
-            cb = F.softmax(b.to(dev), dim=1).max(dim=1)[0]
-            pick = (ca > cb).float().unsqueeze(1)
-            ga, gb = gs * pick, gs * (1 - pick)
-        else:
-            ga, gb = gs * 0.5, gs * 0.5
-        if ctx.has_temp:
-            gt = (-(g * fused).sum() / t).reshape(temperature.shape).to(temperature.dtype).to(temperature.device)
-        return ga.to(a.device), gb.to(b.device), gw, gt, None
+        a, b = ctx.saved_tensors
+        w0, w1, temp, code, raw_w, temperature = ctx.meta
+        ga, gb, dots = ops.fuse_backward(g, a, b, code, w0, w1, temp, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        gw = gt = None
+        need_w = ctx.needs_input_grad[2] and code == _lib.FUSE_WEIGHTED
+        need_t = temperature is not None and ctx.needs_input_grad[3]
+        if need_w or need_t:
+            d = dots.cpu()   # three fp64 scalars
+            if need_w:
+                w = torch.tensor([w0, w1], dtype=torch.float64)
+                # softmax Jacobian: dL/draw_i = w_i * (dot_i - sum_j w_j dot_j)
+                gw = (w * (d[:2] - (w * d[:2]).sum())).to(raw_w.dtype).to(raw_w.device)
+            if need_t:
+                gt = (-d[2] / temp).reshape(temperature.shape).to(temperature.dtype).to(temperature.device)
+        if ga is not None:
+            ga = ga.to(a.dtype).to(a.device)
+        if gb is not None:
+            gb = gb.to(b.dtype).to(b.device)
+        return ga, gb, gw, gt, None
 
 
 class FogDensityAwareLoss(nn.Module):

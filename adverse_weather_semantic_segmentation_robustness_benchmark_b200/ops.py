@@ -250,6 +250,27 @@ def members_n(members, labels: Optional[torch.Tensor] = None, *, ignore_index: i
     return out
 
 
+def fuse_backward(grad_fused: torch.Tensor, logits_a: torch.Tensor, logits_b: torch.Tensor, strategy: int, w0: float,
+                  w1: float, temperature: Optional[float], want_a: bool = True, want_b: bool = True):
+    """awx_fuse_backward: (grad_a | None, grad_b | None, dots fp64[3] device) for the fusion's backward pass."""
+    lib = _lib.load()
+    g = to_device(grad_fused, torch.float32)
+    a = to_device(logits_a, torch.float32)
+    b = to_device(logits_b, torch.float32)
+    if not (g.shape == a.shape == b.shape) or a.dim() != 4:
+        raise ValueError("fuse_backward needs three [B,C,H,W] tensors of equal shape")
+    bsz, ncls, h, w = a.shape
+    ga = torch.empty_like(a) if want_a else None
+    gb = torch.empty_like(b) if want_b else None
+    dots = torch.zeros(3, dtype=torch.float64, device=a.device)
+    ws = torch.empty(int(lib.awx_fuse_backward_workspace_bytes()), dtype=torch.uint8, device=a.device)
+    rc = lib.awx_fuse_backward(_ptr(g), _ptr(a), _ptr(b), _ptr(ga), _ptr(gb), bsz, ncls, h * w, strategy, float(w0), float(w1),
+                               1.0 if temperature is None else float(temperature), 0 if temperature is None else 1,
+                               _ptr(dots), _ptr(ws), _stream())
+    _lib.check(rc, "awx_fuse_backward")
+    return ga, gb, dots
+
+
 def confusion(pred: torch.Tensor, labels: torch.Tensor, num_classes: int, ignore_index: int = 255):
     """(confusion int64 [C,C] device tensor, counters int64 [8] device tensor) from prediction maps."""
     lib = _lib.load()

@@ -238,6 +238,16 @@ int awx_fogloss(const float* logits, const void* labels, int32_t label_dtype,
                 double* sums, float* dlogits, float* ddepth, float* dfog /*nullable*/,
                 int64_t* bad_labels, void* workspace, void* stream);
 
+/* Gradient of EnsembleModel's fusion for training (models/model.py:442-462): with gs = grad_fused / T,
+ * grad_a = gs*w0 | gs/2 | gs*[member a picked], grad_b likewise (either may be NULL), and
+ * dots (device fp64 [3], overwritten) = {sum gs*a, sum gs*b, sum grad_fused*fused}, from which the caller forms the
+ * gradients of the raw ensemble weights (softmax Jacobian) and of the temperature.
+ * workspace: awx_fuse_backward_workspace_bytes() bytes. */
+size_t awx_fuse_backward_workspace_bytes(void);
+int awx_fuse_backward(const float* grad_fused, const float* logits_a, const float* logits_b, float* grad_a, float* grad_b,
+                      int64_t batch, int32_t num_classes, int64_t pixels_per_image, int32_t strategy, float w0, float w1,
+                      float temperature, int32_t use_temperature, double* dots, void* workspace, void* stream);
+
 /* FogDensityAwareLoss._estimate_fog_density_from_depth (models/model.py:644-677) and its gradient:
  * density = clamp(0.7 * (d - min d)/(max d - min d + 1e-8) - 0.3 * [|grad d| > mean |grad d|], 0, 1), min / max /
  * mean over the whole [B,H,W] tensor.  bwd: grad_depth = d(sum grad_density * density)/d depth as autograd

@@ -202,3 +202,43 @@ def test_depth_density_forward_backward(pkg, golden):
     dd = d.detach().clone().cuda().requires_grad_(True)
     (ops_loss.depth_density(dd) * up.cuda()).sum().backward()
     _close(dd.grad.cpu().numpy(), d.grad.numpy(), 2e-5, 1e-7)
+
+
+@pytest.mark.parametrize("strategy", ["weighted_average", "mean", "max_confidence"])
+@pytest.mark.parametrize("ts", [True, False])
+def test_fusion_backward_kernel(pkg, strategy, ts):
+    """awx_fuse_backward (with depth heads: C = 1 through the same kernel) against torch autograd of the
+    reference's fusion expressions, for every strategy, with and without temperature scaling."""
+    from oracle import fusion as of_
+    torch.manual_seed(11)
+    b, c, h, w = 2, 19, 12, 20
+    a0, b0 = torch.randn(b, c, h, w) * 2, torch.randn(b, c, h, w) * 2
+    d10, d20 = torch.rand(b, 1, h, w), torch.rand(b, 1, h, w)
+    up, upd = torch.randn(b, c, h, w), torch.randn(b, 1, h, w)
+
+    a, bb = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    d1, d2 = d10.clone().requires_grad_(True), d20.clone().requires_grad_(True)
+    ens = pkg.EnsembleModel(c, True, strategy, ts, segformer=_Fixed(a, d1), deeplabv3plus=_Fixed(bb, d2))
+    with torch.no_grad():
+        ens.ensemble_weights.copy_(torch.tensor([0.3, 0.9]))
+        if ts:
+            ens.temperature.copy_(torch.tensor([1.7]))
+    ens.train()
+    out = ens(torch.zeros(b, 3, h, w))
+    ((out["segmentation"] * up.cuda()).sum() + (out["depth"] * upd.cuda()).sum()).backward()
+
+    ar, br = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    d1r, d2r = d10.clone().requires_grad_(True), d20.clone().requires_grad_(True)
+    rw = torch.tensor([0.3, 0.9], requires_grad=True)
+    t = torch.tensor([1.7], requires_grad=True)
+    fused = of_.fuse_logits(ar, br, strategy, rw, t if ts else None)
+    depth = of_.fuse_depth(d1r, d2r, strategy, rw)
+    ((fused * up).sum() + (depth * upd).sum()).backward()
+
+    assert torch.equal(out["segmentation"].detach().cpu(), fused.detach())
+    for got, want in ((a.grad, ar.grad), (bb.grad, br.grad), (d1.grad, d1r.grad), (d2.grad, d2r.grad)):
+        _close(got.cpu().numpy(), want.numpy(), 1e-5, 1e-7)
+    if strategy == "weighted_average":
+        _close(ens.ensemble_weights.grad.cpu().numpy(), rw.grad.numpy(), 1e-4, 1e-5)
+    if ts:
+        _close(ens.temperature.grad.cpu().numpy(), t.grad.numpy(), 1e-4, 1e-5)
