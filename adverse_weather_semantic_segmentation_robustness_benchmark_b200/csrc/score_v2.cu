@@ -185,10 +185,21 @@ __device__ __noinline__ void slow_pixel(const ScoreParams& p, const float* s_edg
   o.mi = 0.f;
   o.js = 0.f;
   o.mpred = 0;
-  score_pixel<kC, ENS, JS>(a, b, kC, p, s_edges, ga, gb, p.w0, p.w1, amax, bmax, o);
+  float w0 = p.w0, w1 = p.w1;
+  if (ENS && p.strategy == AWX_FUSE_MAXCONF) {  // member with the larger max-softmax, strict > (model.py:449-455)
+    float sa = 0.f, sb = 0.f;
+    for (int c = 0; c < kC; ++c) {
+      sa += ex2_approx((a[c] - amax) * kLog2e);
+      sb += ex2_approx((b[ENS ? c : 0] - bmax) * kLog2e);
+    }
+    w0 = __frcp_rn(sa) > __frcp_rn(sb) ? 1.f : 0.f;
+    w1 = 1.f - w0;
+  }
+  score_pixel<kC, ENS, JS>(a, b, kC, p, s_edges, ga, gb, w0, w1, amax, bmax, o);
 }
 
-// MODE: 0 single member, 1 weighted average, 2 mean.
+// MODE: 0 single member, 1 weighted average, 2 mean, 3 max-confidence (weighted average with per-pixel weights
+//       (1,0) / (0,1): 1*a + 0*b is the reference's pick*l1 + (1-pick)*l2 operation for operation).
 // FAST: 0 generic (runtime label dtype, optional per-pixel maps, any edges), 1 uint8 labels and bins
 //       only, 2 int64 labels and bins only -- the streaming-evaluation configurations, with every
 //       map / dtype branch compiled out and the ECE edges known to be linspace(0,1,nb+1).
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   const int ignore = p.ignore_index;
   const bool lab_u8 = FAST == 1 || (FAST == 0 && p.label_mode == AWX_LABEL_U8);
   const int div_mode = DIV >= 0 ? DIV : p.div_mode;
-  unsigned n_correct = 0, n_bad = 0, n_ambig = 0;
+  unsigned n_correct = 0, n_bad = 0, n_ambig = 0, n_pick = 0;
   unsigned u = 0, ph = 0, since_flush = 0;
   unsigned* my_lo = w_lo + warp * nb * kEceRep;
   unsigned* my_hi = w_hi + warp * nb * kEceRep;
@@ -386,12 +397,39 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       continue;
     }
 
+    // ---- P0 (max-confidence only): the member with the larger max-softmax supplies the logits
+    float2 w0p = w0, w1p = w1;   // per-pixel fusion weights
+    if (MODE == 3) {
+      float am = a[0].x, bm = b[0].x;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        am = fmaxf(am, fmaxf(a[i].x, a[i].y));
+        bm = fmaxf(bm, fmaxf(b[ENS ? i : 0].x, b[ENS ? i : 0].y));
+      }
+      const float ca0 = -(am * kLog2e), cb0 = -(bm * kLog2e);
+      const float2 ca2 = splat(ca0), cb2 = splat(cb0);
+      float2 s1 = splat(0.f), s2 = splat(0.f);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const float2 ta = fma2(a[i], l2e, ca2), tb = fma2(b[ENS ? i : 0], l2e, cb2);
+        s1 = add2(s1, make_float2(ex2_approx(ta.x), (2 * i + 1 < kC) ? ex2_approx(ta.y) : 0.f));
+        s2 = add2(s2, make_float2(ex2_approx(tb.x), (2 * i + 1 < kC) ? ex2_approx(tb.y) : 0.f));
+      }
+      // confidences 1/S with the shifted-exponent correction (see header)
+      const float ra = rcp_approx(s1.x + s1.y), rb = rcp_approx(s2.x + s2.y);
+      const float ca = fmaf(ra, fmaf(am, kLog2e, ca0) * kLn2, ra), cb = fmaf(rb, fmaf(bm, kLog2e, cb0) * kLn2, rb);
+      const bool pick_a = ca > cb;
+      n_pick += act && fabsf(ca - cb) <= 4.8e-7f * fmaxf(ca, cb);
+      w0p = splat(pick_a ? 1.f : 0.f);
+      w1p = splat(pick_a ? 0.f : 1.f);
+    }
+
     // ---- P1: fused logits (exact), maxima, first arg-max
     float2 v[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-      if (MODE == 1)
-        v[i] = add2(fma2(w0, a[i], nz), fma2(w1, b[ENS ? i : 0], nz));  // three roundings, see header
+      if (MODE == 1 || MODE == 3)
+        v[i] = add2(fma2(w0p, a[i], nz), fma2(w1p, b[ENS ? i : 0], nz));  // three roundings, see header
       else if (MODE == 2)
         v[i] = mul2(add2(a[i], b[ENS ? i : 0]), half);
       else
@@ -576,7 +614,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
           marg = so.mpred;
         } else {
           int amb = 0;
-          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, p.w0, p.w1, div_mode, T, s_edges, nb, &amb);
+          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, w0p.x, w1p.x, div_mode, T, s_edges, nb, &amb);
           ambig = amb;
           bin = ece_bin(conf, s_edges, nb);
         }
@@ -689,10 +727,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
 
   if (!have_labels) return;
   {
-    unsigned vv[3] = {n_correct, n_bad, n_ambig};
-    const int slot[3] = {AWX_CNT_CORRECT, AWX_CNT_BAD_LABEL, AWX_CNT_ECE_AMBIG};
+    unsigned vv[4] = {n_correct, n_bad, n_ambig, n_pick};
+    const int slot[4] = {AWX_CNT_CORRECT, AWX_CNT_BAD_LABEL, AWX_CNT_ECE_AMBIG, AWX_CNT_PICK_AMBIG};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
       const unsigned s = __reduce_add_sync(0xffffffffu, vv[k]);
       if (lane == 0 && s) atomicAdd(&s_cnt[slot[k]], s);
     }
@@ -752,6 +790,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     if (bad) atomicAdd(bins + p.lay.counters + AWX_CNT_BAD_LABEL, (u64)bad);
     if (s_cnt[AWX_CNT_ECE_AMBIG]) atomicAdd(bins + p.lay.counters + AWX_CNT_ECE_AMBIG, (u64)s_cnt[AWX_CNT_ECE_AMBIG]);
     if (s_cnt[AWX_CNT_ENS_WRONG]) atomicAdd(bins + p.lay.counters + AWX_CNT_ENS_WRONG, (u64)s_cnt[AWX_CNT_ENS_WRONG]);
+    if (s_cnt[AWX_CNT_PICK_AMBIG]) atomicAdd(bins + p.lay.counters + AWX_CNT_PICK_AMBIG, (u64)s_cnt[AWX_CNT_PICK_AMBIG]);
     if (nobin) atomicAdd(bins + p.lay.counters + AWX_CNT_NO_BIN, (u64)nobin);
     if (blockIdx.x == 0) atomicAdd(bins + p.lay.counters + AWX_CNT_PIXELS, (u64)(p.B * p.HW));
   }
@@ -823,7 +862,7 @@ int launch_v2_mode(const ScoreParams& p, bool js, cudaStream_t stream) {
 }  // namespace
 
 bool score_v2_supported(const ScoreParams& p) {
-  if (p.C != kC || p.strategy == AWX_FUSE_MAXCONF) return false;
+  if (p.C != kC) return false;
   if (p.HW % 4 != 0) return false;
   if (p.B * p.HW >= (1LL << 32)) return false;  // CTA-level counters are 32 bit
   if (((uintptr_t)p.a & 15) != 0 || ((uintptr_t)p.b & 15) != 0) return false;
@@ -834,6 +873,7 @@ bool score_v2_supported(const ScoreParams& p) {
 int launch_score_v2(const ScoreParams& p, bool ens, bool js, cudaStream_t stream) {
   if (!ens) return launch_v2_mode<0>(p, false, stream);
   if (p.strategy == AWX_FUSE_MEAN) return launch_v2_mode<2>(p, js, stream);
+  if (p.strategy == AWX_FUSE_MAXCONF) return launch_v2_mode<3>(p, js, stream);
   return launch_v2_mode<1>(p, js, stream);
 }
 

@@ -32,5 +32,6 @@ timeit("single (77 B/px)", lambda: ops.score(la, None, tgt, bins=bins1), 77)
 timeit("ens weighted T=1 (153 B/px)", lambda: ops.score(la, lb, tgt, strategy=_lib.FUSE_WEIGHTED, auroc_bins=4096, bins=bins2), 153)
 timeit("ens weighted T=1.7 (153 B/px)", lambda: ops.score(la, lb, tgt, strategy=_lib.FUSE_WEIGHTED, temperature=1.7, auroc_bins=4096, bins=bins2), 153)
 timeit("ens mean noT (153 B/px)", lambda: ops.score(la, lb, tgt, strategy=_lib.FUSE_MEAN, auroc_bins=4096, bins=bins2), 153)
+timeit("ens max_confidence T=1.7 (153 B/px)", lambda: ops.score(la, lb, tgt, strategy=_lib.FUSE_MAXCONF, temperature=1.7, auroc_bins=4096, bins=bins2), 153)
 cp = torch.empty_like(la)
 timeit("torch copy (152 B/px r+w)", lambda: cp.copy_(la), 152)
