@@ -35,8 +35,11 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 __device__ __forceinline__ unsigned to_u8_f64(double v) {
-  v = fmin(fmax(v, 0.0), 1.0);
-  return (unsigned)__double2int_rz(__dmul_rn(v, 255.0));
+  // (np.clip(v, 0, 1) * 255).astype(uint8): truncation toward zero and the clip commute (v * 255 in (-1, 0) and the
+  // clipped 0 both give 0; v > 1 gives >= 255 either way), so the clamp runs on the integer pipe instead of two
+  // fp64 min / max
+  const int i = __double2int_rz(__dmul_rn(v, 255.0));
+  return (unsigned)min(max(i, 0), 255);
 }
 __device__ __forceinline__ unsigned to_u8_f32(float v) {
   v = fminf(fmaxf(v, 0.0f), 1.0f);
