@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
   const double neg_beta = -prm.d0;  // numpy evaluates (-beta) * depth
   const double airlight = prm.d1;   // already rounded to fp32 by the host (A * ones_like(fp32))
   const float gain = prm.f0;
-  const double night_i = prm.d0;
+  const double half_i = prm.d0 * 0.5;  // night: intensity / 2 (exact)
 
   for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const long long px0 = ch * kChunkPx;
@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
               const float shift = c == 0 ? 0.8f : (c == 1 ? 0.85f : 1.2f);
               const float v = __fmul_rn(__fmul_rn(x, gain), shift);
               const double nz = live ? (double)fld[(px0 + p + j) * 3 + c] : 0.0;
-              r = to_u8_f64(__dadd_rn((double)v, __dmul_rn(__dmul_rn(nz, night_i), 0.5)));
+              // noise * I * 0.5: the halving is exact, so fl(fl(nz * I) * 0.5) == fl(nz * (I * 0.5)): one fp64 multiply
+              r = to_u8_f64(__dadd_rn((double)v, __dmul_rn(nz, half_i)));
             }
             ov[k >> 2] |= r << ((k & 3) * 8);
           }
