@@ -226,8 +226,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     score_v2_kernel(const __grid_constant__ ScoreParams p, const int NU, const float negzero) {
   using G = Geo<CW>;
   constexpr int kTP = G::kTP, kCons = G::kCons, kConsWarps = CW, kV2Threads = G::kThreads;
-  constexpr int kUnitFloats = G::kUnitFloats;
   constexpr bool ENS = MODE != 0;
+  // one ring unit = one tile of every member (19 or 38 planes): consumers wait once and release once per tile
+  constexpr int kUnitFloats = (ENS ? 2 : 1) * G::kUnitFloats;
+  constexpr uint32_t kUnitBytes = 4u * kUnitFloats;
   constexpr int NP = (kC + 1) / 2;  // 10 class pairs
   constexpr float kDummy = -1e30f;
   // bins-only kernels: 15 ECE bins and 4096 (ensemble) / 0 (single) AUROC bins are compile-time constants, so
@@ -284,25 +286,25 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long p0 = tin * kTP;
       const unsigned npx = (unsigned)((HW - p0) < kTP ? (HW - p0) : kTP);
+      mbar_wait(empty + u, ph ^ 1u);
+      // ONE thread issues the 19 (38) copies of the unit from warp-uniform operands: the copy instruction takes
+      // uniform registers, and per-lane addresses would make the compiler broadcast every lane's operands one
+      // after the other (ELECT / 4 x R2UR / UBLKCP per copy: ~190 instructions per unit, which kept this warp
+      // busy 70 % of the time)
+      if (elect_one()) {
+        mbar_expect_tx(full + u, (ENS ? 2u : 1u) * kC * npx * 4u);
+        float* dst = units + (size_t)u * kUnitFloats;
 #pragma unroll
-      for (int m = 0; m < (ENS ? 2 : 1); ++m) {
-        mbar_wait(empty + u, ph ^ 1u);
-        // ONE thread issues the 19 copies of the unit from warp-uniform operands: the copy instruction takes
-        // uniform registers, and per-lane addresses would make the compiler broadcast every lane's operands one
-        // after the other (ELECT / 4 x R2UR / UBLKCP per copy: ~190 instructions per unit, which kept this warp
-        // busy 70 % of the time)
-        if (elect_one()) {
-          mbar_expect_tx(full + u, kC * npx * 4u);
+        for (int m = 0; m < (ENS ? 2 : 1); ++m) {
           const float* src = (m == 0 ? p.a : p.b) + img * kC * HW + p0;
-          float* dst = units + (size_t)u * kUnitFloats;
 #pragma unroll
-          for (int c = 0; c < kC; ++c) bulk_load(dst + c * kTP, src + c * HW, npx * 4u, full + u);
+          for (int c = 0; c < kC; ++c) bulk_load(dst + (m * kC + c) * kTP, src + c * HW, npx * 4u, full + u);
         }
-        __syncwarp();
-        if (++u == (unsigned)NU) {
-          u = 0;
-          ph ^= 1u;
-        }
+      }
+      __syncwarp();
+      if (++u == (unsigned)NU) {
+        u = 0;
+        ph ^= 1u;
       }
       tin += gridDim.x;
       while (tin >= tpi) {
@@ -354,26 +356,18 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     float2 a[NP], b[ENS ? NP : 1];
     {
       mbar_wait_a(sbase + 8u * u, ph);
-      const uint32_t s = my_unit0 + u * (uint32_t)G::kUnitBytes;
+      const uint32_t s = my_unit0 + u * kUnitBytes;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         a[i].x = lds_f32(s + (2 * i) * kTP * 4);
         a[i].y = (2 * i + 1 < kC) ? lds_f32(s + (2 * i + 1) * kTP * 4) : kDummy;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(sbase + 8u * (kMaxUnits + u));
-      if (++u == (unsigned)NU) {
-        u = 0;
-        ph ^= 1u;
-      }
-    }
-    if (ENS) {
-      mbar_wait_a(sbase + 8u * u, ph);
-      const uint32_t s = my_unit0 + u * (uint32_t)G::kUnitBytes;
+      if (ENS) {
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        b[ENS ? i : 0].x = lds_f32(s + (2 * i) * kTP * 4);
-        b[ENS ? i : 0].y = (2 * i + 1 < kC) ? lds_f32(s + (2 * i + 1) * kTP * 4) : kDummy;
+        for (int i = 0; i < NP; ++i) {
+          b[ENS ? i : 0].x = lds_f32(s + (kC + 2 * i) * kTP * 4);
+          b[ENS ? i : 0].y = (2 * i + 1 < kC) ? lds_f32(s + (kC + 2 * i + 1) * kTP * 4) : kDummy;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(sbase + 8u * (kMaxUnits + u));
@@ -804,14 +798,15 @@ int launch_v2(const ScoreParams& p, cudaStream_t stream) {
   AWX_CUDA(cudaGetDevice(&dev));
   AWX_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t fixed = v2_ring_offset(CW, p.nb, p.auroc_bins);
-  int nu = (int)(((size_t)max_smem - fixed) / G::kUnitBytes);
-  if (nu > kMaxUnits) nu = kMaxUnits;
+  const size_t unit_bytes = (size_t)(MODE != 0 ? 2 : 1) * G::kUnitBytes;
+  int nu = (int)(((size_t)max_smem - fixed) / unit_bytes);
+  if (nu > kMaxUnits / (MODE != 0 ? 2 : 1)) nu = kMaxUnits / (MODE != 0 ? 2 : 1);
   if (const char* e = getenv("AWX_V2_UNITS")) {  // dev knob: ring depth sensitivity
     const int want = atoi(e);
     if (want >= 2 && want < nu) nu = want;
   }
   AWX_REQUIRE(nu >= 2, AWX_E_UNSUPPORTED, "awx_score v2: histograms leave no room for the TMA ring");
-  const size_t smem = (size_t)nu * G::kUnitBytes + fixed;
+  const size_t smem = (size_t)nu * unit_bytes + fixed;
   AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long ntiles = p.B * ((p.HW + G::kTP - 1) / G::kTP);
   long long blocks = sm_count();
@@ -867,6 +862,9 @@ bool score_v2_supported(const ScoreParams& p) {
   if (p.B * p.HW >= (1LL << 32)) return false;  // CTA-level counters are 32 bit
   if (((uintptr_t)p.a & 15) != 0 || ((uintptr_t)p.b & 15) != 0) return false;
   if (p.labels && p.label_mode == AWX_LABEL_I64 && ((uintptr_t)p.labels & 7) != 0) return false;
+  // two ring units next to the histograms (large ECE x AUROC configurations go to the register-resident kernel)
+  const size_t ring = 2 * (size_t)(p.b ? 2 : 1) * Geo<15>::kUnitBytes;
+  if (v2_ring_offset(15, p.nb, p.auroc_bins) + ring > (size_t)227 * 1024) return false;
   return true;
 }
 

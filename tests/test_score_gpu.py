@@ -242,6 +242,28 @@ def test_accumulation_and_determinism(pkg):
     assert torch.equal(acc.cpu(), whole)
 
 
+def test_largest_bin_configurations_route_and_agree(pkg, monkeypatch):
+    """64 ECE bins x 8192 AUROC bins leave no room for the TMA ring next to the histograms: the call must route
+    to the register-resident kernel (not fail); mid-size configurations must agree between both kernels."""
+    p, ops, _lib = pkg
+    la, lb, tgt = _rand_case(33, 2, 19, 96, 128)
+    for eb, ab in ((64, 8192), (64, 4096), (32, 8192), (15, 8192), (64, 0)):
+        kw = dict(strategy=_lib.FUSE_WEIGHTED, w0=0.3, w1=0.7, temperature=1.2, ece_bins=eb, auroc_bins=ab)
+        monkeypatch.delenv("AWX_SCORE_KERNEL", raising=False)
+        auto = ops.read_bins(ops.score(la, lb, tgt, **kw)["bins"], 19, eb, ab)
+        monkeypatch.setenv("AWX_SCORE_KERNEL", "v1")
+        v1 = ops.read_bins(ops.score(la, lb, tgt, **kw)["bins"], 19, eb, ab)
+        assert np.array_equal(auto.confusion, v1.confusion), (eb, ab)
+        for k in (_lib.CNT_VALID, _lib.CNT_CORRECT, _lib.CNT_PIXELS, _lib.CNT_NO_BIN):
+            assert auto.counter(k) == v1.counter(k), (eb, ab, k)
+        amb = auto.counter(_lib.CNT_ECE_AMBIG) + v1.counter(_lib.CNT_ECE_AMBIG)
+        assert np.abs(auto.ece_count - v1.ece_count).sum() <= 2 * amb, (eb, ab)
+        assert auto.ece_count.sum() == v1.ece_count.sum()
+        np.testing.assert_allclose(auto.ece_conf_sum, v1.ece_conf_sum, rtol=1e-6, atol=1e-3)
+        if ab:
+            assert np.abs(auto.auroc_pos - v1.auroc_pos).sum() + np.abs(auto.auroc_neg - v1.auroc_neg).sum() <= 4
+
+
 def test_full_size_properties(pkg):
     """1024x2048 frames: conservation laws that hold at any size (no oracle needed)."""
     p, ops, _lib = pkg
