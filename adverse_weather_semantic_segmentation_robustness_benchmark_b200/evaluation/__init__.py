@@ -8,10 +8,13 @@ from .metrics import (
 )
 
 from .streaming import StreamingEvaluator, evaluate_model
+from .validation import validate_epoch, estimate_fog_density
 
 __all__ = [
     "StreamingEvaluator",
     "evaluate_model",
+    "validate_epoch",
+    "estimate_fog_density",
     "IoUMetrics",
     "ConfidenceCalibration",
     "EnsembleDisagreementMetrics",

@@ -9,6 +9,7 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows, under
 * Normalize(mean, std) + ToTensorV2           P/data/loader.py:196-199 (albumentations; see below)
 * ConfidenceCalibration.optimize_temperature  P/evaluation/metrics.py:283-321
 * Trainer._estimate_fog_density               P/training/trainer.py:480-511
+* Trainer.validate_epoch                      P/training/trainer.py:377-478
 
 OpenCV / SciPy / NumPy / torch arithmetic is CALLED as the reference calls it.  ``normalize_chw``
 is the exception: albumentations is not installed in the build container (and not vendored in the
@@ -140,6 +141,51 @@ def estimate_fog_density(weather_conditions, h: int, w: int) -> torch.Tensor:
         r = torch.rand(h, w)
         out[i] = r * a + b if b is not None else r * a
     return out
+
+
+def validate_epoch(model, val_loader, loss_fn, num_classes: int = 19, fog_aware: bool = True) -> dict:
+    """The trainer's validation pass (:377-478) on the CPU: per batch the loss (``loss_fn(outputs, targets,
+    fog_density) -> dict`` with the maps of ``estimate_fog_density`` when ``fog_aware``, else
+    ``loss_fn(logits, labels) -> scalar``), sums of ``loss.item() * batch_size`` in Python floats; at the end
+    mIoU of the concatenated argmax maps, overall and for the five fixed weather names (:393-394, :466-476)."""
+    from . import metrics as om
+    sums = {"val_loss": 0.0, "val_seg_loss": 0.0, "val_depth_loss": 0.0, "val_samples": 0}
+    fixed = ("clean", "fog", "rain", "snow", "night")
+    preds, tgts = [], []
+    by_weather = {k: ([], []) for k in fixed}
+    for batch in val_loader:
+        images, labels = batch["image"], batch["label"]
+        weather = batch.get("weather_condition", ["clean"] * images.size(0))
+        outputs = model(images)
+        targets = {"label": labels}
+        if batch.get("depth") is not None:
+            targets["depth"] = batch["depth"]
+        if fog_aware:
+            fd = estimate_fog_density(weather, images.shape[2], images.shape[3]) if len(weather) else None
+            ld = loss_fn(outputs, targets, fd)
+            loss, seg, dep = ld["total_loss"], ld["segmentation_loss"], ld["depth_loss"]
+        else:
+            seg = loss_fn(outputs["segmentation"], labels)
+            loss, dep = seg, 0.0
+        n = images.size(0)
+        sums["val_loss"] += loss.item() * n
+        sums["val_seg_loss"] += seg.item() * n
+        sums["val_depth_loss"] += (dep.item() if isinstance(dep, torch.Tensor) else dep) * n
+        sums["val_samples"] += n
+        p = outputs["segmentation"].argmax(dim=1)
+        preds.append(p)
+        tgts.append(labels)
+        for i, wname in enumerate(weather):
+            if wname in by_weather:
+                by_weather[wname][0].append(p[i:i + 1])
+                by_weather[wname][1].append(labels[i:i + 1])
+    for k in ("val_loss", "val_seg_loss", "val_depth_loss"):
+        sums[k] /= sums["val_samples"]
+    sums["val_miou"] = om.iou(torch.cat(preds), torch.cat(tgts), num_classes)["mean_iou"]
+    for wname, (pl, tl) in by_weather.items():
+        if pl:
+            sums[f"val_miou_{wname}"] = om.iou(torch.cat(pl), torch.cat(tl), num_classes)["mean_iou"]
+    return sums
 
 
 # ------------------------------------------------------------ domain-adaptation augmentation

@@ -248,6 +248,85 @@ def prep_cases():
     np.savez_compressed(os.path.join(HERE, "prep.npz"), **out)
 
 
+def trainer_batches(seed, n_batches, bsz, c, h, w, with_depth, with_other):
+    """Synthetic validation loader + per-batch model outputs (shared with the tests: everything a test needs is
+    stored in the fixture, this only builds it)."""
+    gen = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    names = ["clean", "fog", "rain", "snow", "night"] + (["hail"] if with_other else [])
+    batches = []
+    for _ in range(n_batches):
+        b = {"image": torch.rand(bsz, 3, h, w, generator=gen),
+             "label": torch.randint(0, c, (bsz, h, w), generator=gen),
+             "weather_condition": [names[i] for i in rng.randint(0, len(names), bsz)],
+             "_seg": torch.randn(bsz, c, h, w, generator=gen) * 2}
+        if with_depth:
+            b["depth"] = torch.rand(bsz, h, w, generator=gen) * 50
+            b["_depth"] = torch.rand(bsz, 1, h, w, generator=gen) * 50
+        batches.append(b)
+    return batches
+
+
+def trainer_cases():
+    """SURVEY.md 8f row 1, trainer twin: AdverseWeatherTrainer.validate_epoch / _estimate_fog_density run
+    UNBOUND on a namespace carrying the members they read (model, val_loader, device, loss_fn, metrics)."""
+    from types import SimpleNamespace
+    tr = refshim.trainer()
+    met = refshim.metrics()
+    T = tr.AdverseWeatherTrainer
+    out = {"versions": versions()}
+    # fog-density maps: the global torch CPU generator, one rand(h, w) per frame
+    names = ["fog", "clean", "rain", "snow", "night", "hail", "fog"]
+    torch.manual_seed(123)
+    fd = T._estimate_fog_density(None, {"weather_condition": names, "image": torch.zeros(len(names), 3, 20, 28)})
+    out["fd_names"] = np.array(names)
+    out["fd_maps"] = fd.numpy()
+    assert T._estimate_fog_density(None, {"image": torch.zeros(1, 3, 4, 4)}) is None
+
+    class _Replay(torch.nn.Module):
+        def __init__(self, batches):
+            super().__init__()
+            self.batches, self.i = batches, 0
+
+        def forward(self, x):
+            b = self.batches[self.i]
+            self.i += 1
+            o = {"segmentation": b["_seg"]}
+            if "_depth" in b:
+                o["depth"] = b["_depth"]
+            return o
+
+    cases = {"v_depth": (5, 3, 3, 19, 24, 32, True, True, "cross_entropy"),
+             "v_nodepth": (6, 2, 4, 19, 16, 48, False, False, "cross_entropy"),
+             "v_focal": (7, 2, 2, 7, 20, 20, True, True, "focal")}
+    for tag, (seed, nb, bsz, c, h, w, with_depth, with_other, base) in cases.items():
+        batches = trainer_batches(seed, nb, bsz, c, h, w, with_depth, with_other)
+        ns = SimpleNamespace(model=_Replay(batches), val_loader=batches, device=torch.device("cpu"),
+                             loss_fn=tr.FogDensityAwareLoss(base_loss=base), metrics=met.RobustnessMetrics(c))
+        ns._estimate_fog_density = lambda b: T._estimate_fog_density(ns, b)
+        torch.manual_seed(1000 + seed)
+        res = T.validate_epoch(ns)
+        out[f"{tag}_args"] = np.array([seed, nb, bsz, c, h, w, int(with_depth), int(with_other)])
+        out[f"{tag}_base"] = np.array(base)
+        out[f"{tag}_keys"] = np.array(sorted(res))
+        out[f"{tag}_vals"] = np.array([float(res[k]) for k in sorted(res)], dtype=np.float64)
+        for i, b in enumerate(batches):
+            for k, v in b.items():
+                out[f"{tag}_b{i}_{k}"] = np.array(v) if k == "weather_condition" else v.numpy()
+    # plain criterion (the trainer's non-fog-aware branch, trainer.py:431-434)
+    batches = trainer_batches(9, 2, 3, 19, 16, 24, False, False)
+    ns = SimpleNamespace(model=_Replay(batches), val_loader=batches, device=torch.device("cpu"),
+                         loss_fn=torch.nn.CrossEntropyLoss(), metrics=met.RobustnessMetrics(19))
+    res = T.validate_epoch(ns)
+    out["v_plain_args"] = np.array([9, 2, 3, 19, 16, 24, 0, 0])
+    out["v_plain_keys"] = np.array(sorted(res))
+    out["v_plain_vals"] = np.array([float(res[k]) for k in sorted(res)], dtype=np.float64)
+    for i, b in enumerate(batches):
+        for k, v in b.items():
+            out[f"v_plain_b{i}_{k}"] = np.array(v) if k == "weather_condition" else v.numpy()
+    np.savez_compressed(os.path.join(HERE, "trainer.npz"), **out)
+
+
 if __name__ == "__main__":
     if not refshim.available():
         raise SystemExit("reference not present; golden files can only be regenerated in the build container")
@@ -256,6 +335,7 @@ if __name__ == "__main__":
     fusion_cases()
     loss_cases()
     prep_cases()
+    trainer_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -74,6 +74,17 @@ def loader():
     return _cache["loader"]
 
 
+def trainer():
+    """training/trainer.py imported through the reference package (needs the loader and model shims)."""
+    if "trainer" not in _cache:
+        loader()
+        if "segmentation_models_pytorch" not in sys.modules:
+            sys.modules["segmentation_models_pytorch"] = types.ModuleType("segmentation_models_pytorch")
+        import importlib
+        _cache["trainer"] = importlib.import_module(PKG + ".training.trainer")
+    return _cache["trainer"]
+
+
 def ensemble_with_fixed_members(l1, l2, strategy="weighted_average", temperature_scaling=True,
                                 raw_weights=None, temperature=None, d1=None, d2=None):
     """The reference's EnsembleModel with two tiny producers injected, so that its own

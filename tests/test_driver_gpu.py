@@ -168,3 +168,42 @@ def test_chunked_updates_equal_one_update():
         many.update("x", la[k:k + 2], lb[k:k + 2], lab[k:k + 2])
     assert torch.equal(one.canonical_bins(), many.canonical_bins())
     assert one.finalize() == many.finalize()
+
+
+# ------------------------------------------------------------- trainer twin: validate_epoch (trainer.py:377-511)
+def test_trainer_fog_density_maps_bit_exact(golden):
+    """estimate_fog_density draws from the global torch CPU generator in the reference's order; the affine map
+    runs on the device with the CPU's two roundings."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import estimate_fog_density
+    g = golden("trainer")
+    names = [str(x) for x in g["fd_names"]]
+    torch.manual_seed(123)
+    got = estimate_fog_density({"weather_condition": names, "image": torch.zeros(len(names), 3, 20, 28)})
+    assert got.is_cuda and got.dtype == torch.float32
+    np.testing.assert_array_equal(got.cpu().numpy(), g["fd_maps"])
+    assert estimate_fog_density({"image": torch.zeros(1, 3, 4, 4)}) is None
+
+
+@pytest.mark.parametrize("tag", ["v_depth", "v_nodepth", "v_focal", "v_plain"])
+def test_validate_epoch_matches_reference(golden, tag):
+    """The streaming validation pass against the reference's own validate_epoch (fixture made by running it):
+    mIoU values identical (integer confusion matrices, same finalisation), loss means to fp32 rounding."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import FogDensityAwareLoss, RobustnessMetrics
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import validate_epoch
+    from trainer_fixture import ReplayModel, trainer_fixture_batches
+    g = golden("trainer")
+    seed, nb, bsz, c = (int(x) for x in g[f"{tag}_args"][:4])
+    batches = trainer_fixture_batches(g, tag)
+    dev = torch.device("cuda")
+    if tag == "v_plain":
+        loss_fn = torch.nn.CrossEntropyLoss()
+    else:
+        loss_fn = FogDensityAwareLoss(base_loss=str(g[f"{tag}_base"]))
+        torch.manual_seed(1000 + seed)
+    res = validate_epoch(ReplayModel(batches, dev), batches, loss_fn, RobustnessMetrics(c), dev)
+    assert sorted(res) == [str(k) for k in g[f"{tag}_keys"]]
+    for k, v in zip((str(k) for k in g[f"{tag}_keys"]), g[f"{tag}_vals"]):
+        if "miou" in k or k == "val_samples":
+            assert float(res[k]) == v, k
+        else:
+            assert float(res[k]) == pytest.approx(v, rel=2e-6), k

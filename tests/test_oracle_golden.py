@@ -277,3 +277,35 @@ def test_member_lists_match_reference(golden, tag, n):
     _eq(om.mi_map(members).numpy(), g[f"{tag}_mi"], exact, atol=2e-6, rtol=1e-5)
     _eq(om.variance_map(members).numpy(), g[f"{tag}_var"], exact, atol=1e-7, rtol=1e-5)
     assert om.disagreement_auroc(members, targets) == float(g[f"{tag}_auroc"])
+
+
+# ------------------------------------------------- trainer twin (8f row 1): validation pass + fog-density maps
+from trainer_fixture import ReplayModel, trainer_fixture_batches  # noqa: E402
+
+
+def test_trainer_fog_density_maps_match_reference(golden):
+    g = golden("trainer")
+    torch.manual_seed(123)
+    got = op.estimate_fog_density([str(x) for x in g["fd_names"]], 20, 28)
+    np.testing.assert_array_equal(got.numpy(), g["fd_maps"])
+
+
+@pytest.mark.parametrize("tag", ["v_depth", "v_nodepth", "v_focal", "v_plain"])
+def test_validate_epoch_matches_reference(golden, tag):
+    g = golden("trainer")
+    seed, nb, bsz, c = (int(x) for x in g[f"{tag}_args"][:4])
+    batches = trainer_fixture_batches(g, tag)
+    if tag == "v_plain":
+        res = op.validate_epoch(ReplayModel(batches), batches, torch.nn.CrossEntropyLoss(), c, fog_aware=False)
+    else:
+        base = str(g[f"{tag}_base"])
+        torch.manual_seed(1000 + seed)
+        res = op.validate_epoch(ReplayModel(batches), batches,
+                                lambda o, t, fd: ol.fog_loss(o, t, fd, base_loss=base), c)
+    assert sorted(res) == [str(k) for k in g[f"{tag}_keys"]]
+    want = dict(zip((str(k) for k in g[f"{tag}_keys"]), g[f"{tag}_vals"]))
+    for k, v in want.items():
+        if "miou" in k or k == "val_samples":
+            assert float(res[k]) == v, k
+        else:
+            assert float(res[k]) == pytest.approx(v, rel=1e-6), k
