@@ -280,10 +280,29 @@ class Workload:
         self.ev.all_reduce()
 
 
+def bind_near_gpu(local_rank, world):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as closest to its GPU, so that the pinned
+    staging buffers of the e2e leg are allocated on that socket (first touch) and every rank's H2D copies stay
+    off the inter-socket link.  Single-rank runs keep all cores (the cpu_baseline leg uses them)."""
+    if world <= 1:
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import numpy as np
     import torch
     import torch.distributed as dist
+    near_cpus = bind_near_gpu(local_rank, world)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -333,6 +352,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, wl, device, world, barrier, max_over_ranks, px_step)
+        if near_cpus is not None:
+            e2e["cpu_affinity"] = "rank pinned to the %d CPUs NVML reports closest to its GPU" % near_cpus
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
