@@ -1,10 +1,11 @@
 // awx_score, kernel v2 (C == 19): TMA-staged, register-resident, packed-fp32 scoring.
 //
-// One persistent CTA per SM: warp 15 is the producer, warps 0-14 (480 threads) consume.
-//   producer  walks the CTA's tiles (480 consecutive pixels of one image) and, per member, issues 19
-//             bulk async copies (cp.async.bulk, one 1.9 KB plane segment each) into the next free unit of
-//             a shared-memory ring, completing on that unit's mbarrier.  The ring holds 4-5 units of
-//             36 KB, i.e. up to ~180 KB per SM in flight independent of what the consumers do.
+// One persistent CTA per SM: the last warp is the producer, warps 0..CW-1 (480 or 608 threads) consume.
+//   producer  walks the CTA's tiles (32*CW consecutive pixels of one image) and, per tile, issues 19 bulk
+//             async copies per member (cp.async.bulk, one 1.9 KB plane segment each) into the next free
+//             unit of a shared-memory ring, completing on that unit's mbarrier.  A unit is one tile of every
+//             member (36 / 46 KB for one member, 73 KB for two); the ring holds 4 (one member) or 2 (two
+//             members) of them, i.e. ~146-185 KB per SM in flight independent of what the consumers do.
 //   consumer  thread t owns pixel t of the tile: after the unit's barrier flips it pulls its 19 (or 38)
 //             values into registers with immediate-offset LDS and releases the unit at once, so
 //             shared memory is only a landing zone.  Element-wise arithmetic runs on float2 PAIRS OF
@@ -36,8 +37,9 @@ struct Geo {
   static constexpr int kUnitFloats = kC * kTP;
   static constexpr int kUnitBytes = kUnitFloats * 4;
 };
-constexpr int kMaxUnits = 4;                    // ring depth: 3, 4 and 5 units measure the same; the shared memory is
-                                                // better spent on conflict-free statistics
+constexpr int kMaxUnits = 4;                    // ring depth for one member (2 units of both members for an ensemble):
+                                                // 1.5, 2 and 2.5 tiles measure the same; the shared memory is better
+                                                // spent on conflict-free statistics
 constexpr int kFastEceBins = 15, kFastAurocBins = 4096;  // the streaming evaluator's configuration
 constexpr int kSingleWarps = 19;                // consumer warps of the bins-only single-member kernels
 constexpr unsigned kFlushPixels = 60000;        // per-warp confidence sums are flushed before 2^16 pixels
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         lab = (l >= -2147483647LL && l <= 2147483647LL) ? (int)l : (ignore == -2 ? -3 : -2);
       }
     }
-    // ---- pull the pixel's 19 (+19) values into registers, release the ring units at once
+    // ---- pull the pixel's 19 (+19) values into registers, release the ring unit at once
     float2 a[NP], b[ENS ? NP : 1];
     {
       mbar_wait_a(sbase + 8u * u, ph);
