@@ -42,8 +42,11 @@ __device__ __forceinline__ unsigned to_u8_f64(double v) {
   return (unsigned)min(max(i, 0), 255);
 }
 __device__ __forceinline__ unsigned to_u8_f32(float v) {
-  v = fminf(fmaxf(v, 0.0f), 1.0f);
-  return (unsigned)__float2int_rz(__fmul_rn(v, 255.0f));
+  // (np.clip(v, 0, 1) * 255).astype(uint8): the clip commutes with the truncation (see to_u8_f64), and the
+  // float -> u8 conversion saturates to [0, 255] by itself: one FMUL + one F2I
+  unsigned r;
+  asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(__fmul_rn(v, 255.0f)));
+  return r;
 }
 
 // Optional fused epilogue: albumentations Normalize + ToTensorV2 (data/loader.py:196-199) of the corrupted
@@ -223,7 +226,7 @@ constexpr int kPreW = (kTileW + 2 * kUnitPx) * 3 + 4;  // s_pre row: tile + one 
 constexpr int kRowE = kTileW * 3;                    // output elements per tile row
 constexpr int kHBlock = 12;                          // elements per horizontal-pass task
 
-template <int R>
+template <int R, bool RAIN>
 __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
                                                              const AwxCorruptParams* __restrict__ params,
                                                              const unsigned* __restrict__ mask, int H, int W, int WW,
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   constexpr int PH = kTileH + 2 * R;
   const int b = blockIdx.z;
   const AwxCorruptParams prm = params[b];
-  if ((prm.kind != AWX_RAIN && prm.kind != AWX_SNOW) || prm.blur_k != 2 * R + 1) return;
+  if (prm.kind != (RAIN ? AWX_RAIN : AWX_SNOW) || prm.blur_k != 2 * R + 1) return;
 
   extern __shared__ __align__(16) unsigned char smem[];
   float* s_pre = reinterpret_cast<float*>(smem);  // [PH][kPreW] point-op'ed, overlaid, fp32
@@ -241,13 +244,12 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   const uint8_t* src = img + (size_t)b * H * W * 3;
   uint8_t* dst = out ? out + (size_t)b * H * W * 3 : nullptr;
   const unsigned* m = mask + (size_t)b * H * WW;
-  const bool rain = prm.kind == AWX_RAIN;
   const float k1 = prm.f0, k2 = prm.f1;  // rain: x*k1 + k2 ; snow: clip(x + k1)
   const bool vec_ok = ((W * 3) & 15) == 0 && (((uintptr_t)src) & 15) == 0;
 
   auto point = [&](unsigned u8, int c, bool over) -> float {
     const float x = unit_of_u8(u8);
-    if (rain) {
+    if (RAIN) {
       const float v = __fadd_rn(__fmul_rn(x, k1), k2);
       return over ? (c == 0 ? 0.8f : (c == 1 ? 0.9f : 1.0f)) : v;
     }
@@ -256,13 +258,12 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   };
 
   // ---- stage 1: load units, point op, overlay -> s_pre
-  // task order: 4 rows x UPR units per group, rows fastest, so that a quarter warp (4 rows x 2 units)
-  // writes 8 distinct 16-byte bank groups and a warp still reads 8 consecutive units of each row
-  constexpr int UPR = kTileW / kUnitPx + 2;  // units per staged row
-  for (int i = threadIdx.x; i < ((PH + 3) / 4) * 4 * UPR; i += kBlurThreads) {
-    const int grp = i / (4 * UPR), j = i - grp * (4 * UPR);
-    const int ry = grp * 4 + (j & 3), un = j >> 2;
-    if (ry >= PH) continue;
+  // Interior units first: a warp takes 4 rows x 8 units (rows fastest), so that a quarter warp (4 rows x 2 units)
+  // writes 8 distinct 16-byte bank groups and the warp still reads 8 consecutive units of each row.  The two halo
+  // units of a row only contribute their R <= 3 pixels next to the tile: one 16-byte chunk each, in a second loop
+  // (in the same loop their lanes would idle through the other two chunks of the interior lanes).
+  constexpr int UPR = kTileW / kUnitPx + 2;  // units per staged row (8 interior + 2 halo)
+  auto stage_unit = [&](int ry, int un, int q_lo, int q_hi) {
     const int sy = reflect101(y0 + ry - R, H);
     const int ux = x0 + (un - 1) * kUnitPx;  // first pixel of the unit (may be outside the image)
     float* o = s_pre + ry * kPreW + un * (kUnitPx * 3);
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
       const unsigned mw = m[(size_t)sy * WW + (ux >> 5)] >> (ux & 31);  // bit j = pixel ux + j
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
+        if (q < q_lo || q > q_hi) continue;
         const uint4 w = ld_stream_u4(g + 16 * q);
         const unsigned ws[4] = {w.x, w.y, w.z, w.w};
         float f[16];
@@ -294,6 +296,24 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
 #pragma unroll
         for (int c = 0; c < 3; ++c) o[j * 3 + c] = point(px[c], c, over);
       }
+    }
+  };
+  constexpr int UI = UPR - 2;
+  constexpr int NI = ((PH + 3) / 4) * 4 * UI;  // interior tasks (rows padded to a multiple of 4)
+  static_assert(NI + 2 * PH <= kBlurThreads, "one task per thread: all global loads of the tile are in flight at once");
+  {
+    const int i = threadIdx.x;
+    if (i < NI) {
+      const int grp = i / (4 * UI), j = i - grp * (4 * UI);
+      const int ry = grp * 4 + (j & 3);
+      if (ry < PH) stage_unit(ry, 1 + (j >> 2), 0, 2);
+    } else if (i < NI + 2 * PH) {
+      // halo: the last chunk (pixels 10.67 .. 15) of the left unit, the first chunk (pixels 0 .. 5.33) of the right one
+      const int h = i - NI, ry = h >> 1;
+      if (h & 1)
+        stage_unit(ry, UPR - 1, 0, 0);
+      else
+        stage_unit(ry, 0, 2, 2);
     }
   }
   __syncthreads();
@@ -348,6 +368,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
   constexpr int CG = kRowE / 4;  // 96 column groups
   constexpr int VR = 8;          // output rows per task
   const bool st32 = ((W * 3) & 3) == 0 && (((uintptr_t)dst) & 3) == 0;
+  const size_t row_bytes = (size_t)W * 3;
   unsigned* s_o = reinterpret_cast<unsigned*>(s_pre);  // [kTileH][CG] packed output bytes (norm epilogue only)
   for (int i = threadIdx.x; i < CG * (kTileH / VR); i += kBlurThreads) {
     const int half = i / CG, cg = i - half * CG;
@@ -355,6 +376,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
     float4 win[VR + 2 * R];
 #pragma unroll
     for (int k = 0; k < VR + 2 * R; ++k) win[k] = pv[k * (kRowE / 4)];
+    uint8_t* drow = dst ? dst + ((size_t)(y0 + half * VR) * W + x0) * 3 + cg * 4 : nullptr;  // first output row of the task
 #pragma unroll
     for (int rr = 0; rr < VR; ++rr) {
       const int ry = half * VR + rr;
@@ -379,7 +401,7 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
       // writes below need 4 pixels of ONE channel per thread to be vector stores
       if (norm.ptr) s_o[ry * CG + cg] = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
       if (dst) {
-        uint8_t* d = dst + ((size_t)(y0 + ry) * W + x0) * 3 + cg * 4;
+        uint8_t* d = drow + (size_t)rr * row_bytes;
         if (st32 && cg * 4 + 3 < tw3) {
           *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
         } else {
@@ -430,10 +452,10 @@ constexpr size_t blur_smem() {
   return (size_t)(kTileH + 2 * R) * (kPreW + kRowE) * sizeof(float);
 }
 
-template <int R>
+template <int R, bool RAIN>
 int launch_blur(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparams, const unsigned* mask, int64_t B, int H,
                 int W, int WW, const NormOut& norm, cudaStream_t s) {
-  auto kern = blur_kernel<R>;
+  auto kern = blur_kernel<R, RAIN>;
   AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem<R>()));
   dim3 grid((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, (unsigned)B);
   kern<<<grid, kBlurThreads, blur_smem<R>(), s>>>(img, out, dparams, mask, H, W, WW, norm);
@@ -507,7 +529,7 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
   AWX_REQUIRE(img && (out || norm.ptr) && params && workspace, AWX_E_ARG, "awx_corrupt: NULL pointer (img/out/params/workspace)");
   AWX_REQUIRE(batch <= 65535, AWX_E_UNSUPPORTED, "awx_corrupt: batch %lld > 65535 per call", (long long)batch);
   AWX_REQUIRE(field_dtype == AWX_F32 || field_dtype == AWX_F64, AWX_E_ARG, "awx_corrupt: unknown field dtype %d", field_dtype);
-  bool any_point = false, any_overlay = false, blur3 = false, blur7 = false;
+  bool any_point = false, any_overlay = false, blur[4] = {false, false, false, false};  // rain 3 / 7, snow 3 / 7
   for (int64_t b = 0; b < batch; ++b) {
     const AwxCorruptParams& q = params[b];
     switch (q.kind) {
@@ -525,7 +547,7 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
         AWX_REQUIRE(q.item_count >= 0 && q.item_begin >= 0 && (int64_t)q.item_begin + q.item_count <= n_items, AWX_E_ARG,
                     "awx_corrupt: image %lld item range [%d,+%d) outside %lld items", (long long)b, q.item_begin, q.item_count, (long long)n_items);
         AWX_REQUIRE(q.item_count == 0 || items != nullptr, AWX_E_ARG, "awx_corrupt: items is NULL");
-        (q.blur_k == 3 ? blur3 : blur7) = true;
+        blur[(q.kind == AWX_RAIN ? 0 : 2) + (q.blur_k == 3 ? 0 : 1)] = true;
         break;
       default:
         set_error("awx_corrupt: unknown kind %d for image %lld", q.kind, (long long)b);
@@ -555,9 +577,11 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
     AWX_CUDA(cudaGetLastError());
   note_launch();
     int rc = AWX_OK;
-    if (blur3) rc = launch_blur<1>(img, out, dparams, mask, batch, H, W, WW, norm, s);
-    if (rc != AWX_OK) return rc;
-    if (blur7) rc = launch_blur<3>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+    // one launch per (kind, blur size) present in the batch; every CTA of a launch skips the images of the others
+    if (blur[0]) rc = launch_blur<1, true>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+    if (rc == AWX_OK && blur[1]) rc = launch_blur<3, true>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+    if (rc == AWX_OK && blur[2]) rc = launch_blur<1, false>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+    if (rc == AWX_OK && blur[3]) rc = launch_blur<3, false>(img, out, dparams, mask, batch, H, W, WW, norm, s);
     if (rc != AWX_OK) return rc;
   }
   return AWX_OK;
