@@ -324,3 +324,13 @@ class DepthEstimationPreprocessor:
         """:369-384 (a handful of host scalars per call in the reference's users; kept as NumPy)."""
         return baseline / np.maximum(depth, 1e-6)
 
+    def preprocess_depth_for_training(self, depth: np.ndarray, target_size) -> torch.Tensor:
+        """:386-411: resize to (height, width) if needed, min-max normalise in the array's dtype, fp32 tensor.
+        Per-sample dataset-side work outside the hot path (the dataset's ``__getitem__``), kept on the host
+        with the reference's own calls so that the class is complete."""
+        if depth.shape != tuple(target_size):
+            import cv2
+            depth = cv2.resize(depth, (target_size[1], target_size[0]))
+        lo = np.min(depth)
+        return torch.from_numpy((depth - lo) / (np.max(depth) - lo + 1e-8)).float()
+
