@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     }
     // ---- pull the pixel's 19 (+19) values into registers, release the ring unit at once
     float2 a[NP], b[ENS ? NP : 1];
+    uint32_t held_unit, held_bar;
     {
       mbar_wait_a(sbase + 8u * u, ph);
       const uint32_t s = my_unit0 + u * kUnitBytes;
@@ -371,8 +372,13 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
           b[ENS ? i : 0].y = (2 * i + 1 < kC) ? lds_f32(s + (kC + 2 * i + 1) * kTP * 4) : kDummy;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive_a(sbase + 8u * (kMaxUnits + u));
+      // max-confidence kernels keep the unit until the winning member's logits have been re-read (see P0)
+      held_unit = s;
+      held_bar = sbase + 8u * (kMaxUnits + u);
+      if (MODE != 3) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(held_bar);
+      }
       if (++u == (unsigned)NU) {
         u = 0;
         ph ^= 1u;
@@ -385,6 +391,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
 #pragma unroll
       for (int i = 0; i < NP; ++i) acc += a[i].x + a[i].y + (ENS ? b[ENS ? i : 0].x + b[ENS ? i : 0].y : 0.f);
       if (acc == 1234.5678f) n_bad += 1;
+      if (MODE == 3) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(held_bar);
+      }
       tin += gridDim.x;
       while (tin >= tpiu) {
         tin -= tpiu;
@@ -393,108 +403,13 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       continue;
     }
 
-    // ---- P0 (max-confidence only): the member with the larger max-softmax supplies the logits
-    float2 w0p = w0, w1p = w1;   // per-pixel fusion weights
-    if (MODE == 3) {
-      float am = a[0].x, bm = b[0].x;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        am = fmaxf(am, fmaxf(a[i].x, a[i].y));
-        bm = fmaxf(bm, fmaxf(b[ENS ? i : 0].x, b[ENS ? i : 0].y));
-      }
-      const float ca0 = -(am * kLog2e), cb0 = -(bm * kLog2e);
-      const float2 ca2 = splat(ca0), cb2 = splat(cb0);
-      float2 s1 = splat(0.f), s2 = splat(0.f);
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        const float2 ta = fma2(a[i], l2e, ca2), tb = fma2(b[ENS ? i : 0], l2e, cb2);
-        s1 = add2(s1, make_float2(ex2_approx(ta.x), (2 * i + 1 < kC) ? ex2_approx(ta.y) : 0.f));
-        s2 = add2(s2, make_float2(ex2_approx(tb.x), (2 * i + 1 < kC) ? ex2_approx(tb.y) : 0.f));
-      }
-      // confidences 1/S with the shifted-exponent correction (see header)
-      const float ra = rcp_approx(s1.x + s1.y), rb = rcp_approx(s2.x + s2.y);
-      const float ca = fmaf(ra, fmaf(am, kLog2e, ca0) * kLn2, ra), cb = fmaf(rb, fmaf(bm, kLog2e, cb0) * kLn2, rb);
-      const bool pick_a = ca > cb;
-      n_pick += act && fabsf(ca - cb) <= 4.8e-7f * fmaxf(ca, cb);
-      w0p = splat(pick_a ? 1.f : 0.f);
-      w1p = splat(pick_a ? 0.f : 1.f);
-    }
-
-    // ---- P1: fused logits (exact), maxima, first arg-max
-    float2 v[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      if (MODE == 1 || MODE == 3)
-        v[i] = add2(fma2(w0p, a[i], nz), fma2(w1p, b[ENS ? i : 0], nz));  // three roundings, see header
-      else if (MODE == 2)
-        v[i] = mul2(add2(a[i], b[ENS ? i : 0]), half);
-      else
-        v[i] = a[i];
-    }
-    if (div_mode == 2) {
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        v[i].x = __fdiv_rn(v[i].x, T);
-        if (2 * i + 1 < kC) v[i].y = __fdiv_rn(v[i].y, T);
-      }
-    }
-    float vmax = v[0].x, amax = a[0].x, bmax = b[0].x;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      vmax = fmaxf(vmax, fmaxf(v[i].x, v[i].y));
-      if (ENS) {
-        amax = fmaxf(amax, fmaxf(a[i].x, a[i].y));
-        bmax = fmaxf(bmax, fmaxf(b[ENS ? i : 0].x, b[ENS ? i : 0].y));
-      }
-    }
-    // first index attaining the max.  With a division by T > 0 still pending (div_mode 1) the
-    // quotient can merge the max with the one or two floats just below it (at most 3 inputs share
-    // a quotient); torch's argmax over the divided logits returns the first of those, so compare
-    // against the smallest float whose quotient equals the max quotient.
-    float vlo = vmax;
-    if (div_mode == 1) {
-      // branch-free exact quotients; |vmax| outside [1e-25, 1e25] is routed to the scalar slow
-      // path below (residual underflow / quotient overflow), so this block stays straight-line
-      float c1, c2;
-      float_prev2(vmax, c1, c2);
-      const float zmax = div_by_T(vmax, T, p.rT), z1 = div_by_T(c1, T, p.rT), z2 = div_by_T(c2, T, p.rT);
-      vlo = (z1 == zmax) ? ((z2 == zmax) ? c2 : c1) : vmax;
-    }
-    int arg = 0;
-#pragma unroll
-    for (int i = NP - 1; i >= 0; --i) {
-      if (2 * i + 1 < kC) arg = (v[i].y >= vlo) ? 2 * i + 1 : arg;
-      arg = (v[i].x >= vlo) ? 2 * i : arg;
-    }
-
-    // optional fused-logit output (bit exact: div_mode is 0 or 2 whenever it is requested)
-    if (FAST == 0 && p.fused != nullptr && act) {
-      float* fo = p.fused + ((long long)img * kC * HW + p0 + t);
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        fo[(2 * i) * HW] = v[i].x;
-        if (2 * i + 1 < kC) fo[(2 * i + 1) * HW] = v[i].y;
-      }
-    }
-
-    // ---- P3: softmax denominator of the fused logits (shifted exponents, see header)
-    float sz, zdelta;
-    {
-      const float cz = -(vmax * p.kz);
-      zdelta = fmaf(vmax, p.kz, cz) * kLn2;  // exact residual of the rounded product, in nats
-      float2 sz2 = splat(0.f);
-      const float2 cz2 = splat(cz);
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        const float2 x = fma2(v[i], kz, cz2);
-        sz2 = add2(sz2, make_float2(ex2_approx(x.x), (2 * i + 1 < kC) ? ex2_approx(x.y) : 0.f));
-      }
-      sz = sz2.x + sz2.y;
-    }
-
-    // ---- members: softmax sums, entropies, mean probabilities (log2 domain, shifted exponents)
+    // ---- members: softmax sums, entropies, mean probabilities (log2 domain, shifted exponents).  Consumes a[] / b[]
+    // (overwritten in place by the exponentials, then by the unnormalised mean probabilities).  Runs after the
+    // fused-logit phases, except in the max-confidence kernels, where its sums decide which member is scored.
     float mi = 0.f, js = 0.f, sa = 1.f, sb = 1.f;
+    float amax = a[0].x, bmax = b[0].x;
     int marg = 0;
+    auto members_phase = [&]() {
     if (ENS) {
       float2 sa2 = splat(0.f), sb2 = splat(0.f), ta2 = splat(0.f), tb2 = splat(0.f), xab2 = splat(0.f), xba2 = splat(0.f);
       const float2 ca2 = splat(-(amax * kLog2e)), cb2 = splat(-(bmax * kLog2e));
@@ -560,6 +475,112 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         js = kLn2 * (mlm - 0.5f * (mlp + mlq));
       }
     }
+    };
+
+    // ---- P0 (max-confidence only): the member with the larger max-softmax supplies the logits.  The members
+    // phase runs first -- its softmax sums ARE the two confidences -- and the winner's 19 logits are then read
+    // again from the ring unit, which is released only now (one set of member exponentials instead of two).
+    float2 v[NP];
+    float w0s = w0.x, w1s = w1.x;  // per-pixel fusion weights (the exact slow path re-fuses from global memory)
+    if (MODE == 3) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        amax = fmaxf(amax, fmaxf(a[i].x, a[i].y));
+        bmax = fmaxf(bmax, fmaxf(b[ENS ? i : 0].x, b[ENS ? i : 0].y));
+      }
+      members_phase();
+      // confidences 1/S with the shifted-exponent correction (see header)
+      const float ca0 = -(amax * kLog2e), cb0 = -(bmax * kLog2e);
+      const float ra = rcp_approx(sa), rb = rcp_approx(sb);
+      const float ca = fmaf(ra, fmaf(amax, kLog2e, ca0) * kLn2, ra), cb = fmaf(rb, fmaf(bmax, kLog2e, cb0) * kLn2, rb);
+      const bool pick_a = ca > cb;
+      n_pick += act && fabsf(ca - cb) <= 4.8e-7f * fmaxf(ca, cb);
+      w0s = pick_a ? 1.f : 0.f;
+      w1s = pick_a ? 0.f : 1.f;
+      const uint32_t sv = held_unit + (pick_a ? 0u : (uint32_t)(kC * kTP * 4));
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i].x = lds_f32(sv + (2 * i) * kTP * 4);
+        v[i].y = (2 * i + 1 < kC) ? lds_f32(sv + (2 * i + 1) * kTP * 4) : kDummy;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(held_bar);
+    }
+
+    // ---- P1: fused logits (exact), maxima, first arg-max
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      if (MODE == 3)
+        break;  // v already holds the winning member's logits
+      if (MODE == 1)
+        v[i] = add2(fma2(w0, a[i], nz), fma2(w1, b[ENS ? i : 0], nz));  // three roundings, see header
+      else if (MODE == 2)
+        v[i] = mul2(add2(a[i], b[ENS ? i : 0]), half);
+      else
+        v[i] = a[i];
+    }
+    if (div_mode == 2) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i].x = __fdiv_rn(v[i].x, T);
+        if (2 * i + 1 < kC) v[i].y = __fdiv_rn(v[i].y, T);
+      }
+    }
+    float vmax = v[0].x;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      vmax = fmaxf(vmax, fmaxf(v[i].x, v[i].y));
+      if (ENS && MODE != 3) {
+        amax = fmaxf(amax, fmaxf(a[i].x, a[i].y));
+        bmax = fmaxf(bmax, fmaxf(b[ENS ? i : 0].x, b[ENS ? i : 0].y));
+      }
+    }
+    // first index attaining the max.  With a division by T > 0 still pending (div_mode 1) the
+    // quotient can merge the max with the one or two floats just below it (at most 3 inputs share
+    // a quotient); torch's argmax over the divided logits returns the first of those, so compare
+    // against the smallest float whose quotient equals the max quotient.
+    float vlo = vmax;
+    if (div_mode == 1) {
+      // branch-free exact quotients; |vmax| outside [1e-25, 1e25] is routed to the scalar slow
+      // path below (residual underflow / quotient overflow), so this block stays straight-line
+      float c1, c2;
+      float_prev2(vmax, c1, c2);
+      const float zmax = div_by_T(vmax, T, p.rT), z1 = div_by_T(c1, T, p.rT), z2 = div_by_T(c2, T, p.rT);
+      vlo = (z1 == zmax) ? ((z2 == zmax) ? c2 : c1) : vmax;
+    }
+    int arg = 0;
+#pragma unroll
+    for (int i = NP - 1; i >= 0; --i) {
+      if (2 * i + 1 < kC) arg = (v[i].y >= vlo) ? 2 * i + 1 : arg;
+      arg = (v[i].x >= vlo) ? 2 * i : arg;
+    }
+
+    // optional fused-logit output (bit exact: div_mode is 0 or 2 whenever it is requested)
+    if (FAST == 0 && p.fused != nullptr && act) {
+      float* fo = p.fused + ((long long)img * kC * HW + p0 + t);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        fo[(2 * i) * HW] = v[i].x;
+        if (2 * i + 1 < kC) fo[(2 * i + 1) * HW] = v[i].y;
+      }
+    }
+
+    // ---- P3: softmax denominator of the fused logits (shifted exponents, see header)
+    float sz, zdelta;
+    {
+      const float cz = -(vmax * p.kz);
+      zdelta = fmaf(vmax, p.kz, cz) * kLn2;  // exact residual of the rounded product, in nats
+      float2 sz2 = splat(0.f);
+      const float2 cz2 = splat(cz);
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const float2 x = fma2(v[i], kz, cz2);
+        sz2 = add2(sz2, make_float2(ex2_approx(x.x), (2 * i + 1 < kC) ? ex2_approx(x.y) : 0.f));
+      }
+      sz = sz2.x + sz2.y;
+    }
+
+    if (MODE != 3) members_phase();
 
     // ---- confidence, ECE bin, slow paths
     int pred = arg, bin, ambig = 0;
@@ -610,7 +631,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
           marg = so.mpred;
         } else {
           int amb = 0;
-          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, w0p.x, w1p.x, div_mode, T, s_edges, nb, &amb);
+          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, w0s, w1s, div_mode, T, s_edges, nb, &amb);
           ambig = amb;
           bin = ece_bin(conf, s_edges, nb);
         }
