@@ -503,6 +503,19 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         v[i].x = lds_f32(sv + (2 * i) * kTP * 4);
         v[i].y = (2 * i + 1 < kC) ? lds_f32(sv + (2 * i + 1) * kTP * 4) : kDummy;
       }
+      if (FAST == 0 && p.fused != nullptr) {
+        // the fused-logit MAP is the reference's expression as written, mask*l1 + (1-mask)*l2: the other member
+        // enters as 0 * x (a signed zero, or NaN for an infinite logit)
+        const uint32_t so = held_unit + (pick_a ? (uint32_t)(kC * kTP * 4) : 0u);
+        const float2 zero = splat(0.f);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          float2 other;
+          other.x = lds_f32(so + (2 * i) * kTP * 4);
+          other.y = (2 * i + 1 < kC) ? lds_f32(so + (2 * i + 1) * kTP * 4) : 0.f;
+          v[i] = add2(v[i], fma2(zero, other, nz));
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(held_bar);
     }

@@ -206,6 +206,41 @@ def test_ties_nan_and_degenerate(pkg):
     assert int(e["bins"].sum()) == 0
 
 
+@pytest.mark.parametrize("strategy", ["weighted_average", "max_confidence", "mean"])
+def test_ensemble_non_finite_logits_follow_the_reference(pkg, strategy):
+    """+-inf / NaN logits in either member: the prediction map is the arg-max of the reference's own fusion
+    expression (0 * inf = NaN in max_confidence's `mask*l1 + (1-mask)*l2` included; NaN wins torch's arg-max),
+    whatever member ends up being picked, and finite neighbours are untouched."""
+    p, ops, _lib = pkg
+    gen = torch.Generator().manual_seed(5)
+    la = torch.randn(1, 19, 16, 32, generator=gen) * 2
+    lb = torch.randn(1, 19, 16, 32, generator=gen) * 2
+    la[0, :, 0, :] += 3 * torch.nn.functional.one_hot(torch.arange(32) % 19, 19).T   # member 1 confident on row 0
+    lb[0, :, 1, :] += 3 * torch.nn.functional.one_hot(torch.arange(32) % 19, 19).T   # member 2 confident on row 1
+    inf = float("inf")
+    for row in (0, 1, 2):
+        la[0, 4, row, 3], lb[0, 6, row, 5] = -inf, -inf       # -inf in member 1 / member 2
+        la[0, 2, row, 9], lb[0, 8, row, 11] = inf, inf          # +inf
+        la[0, 1, row, 15], lb[0, 3, row, 17] = float("nan"), float("nan")
+        la[0, 5, row, 21], lb[0, 5, row, 21] = -inf, inf        # both members at one pixel
+    tgt = torch.randint(0, 19, (1, 16, 32), generator=gen)
+    raw_w = torch.tensor([0.3, 0.9])
+    w = of_.member_weights(raw_w)
+    code = {"weighted_average": _lib.FUSE_WEIGHTED, "max_confidence": _lib.FUSE_MAXCONF, "mean": _lib.FUSE_MEAN}[strategy]
+    want = of_.fuse_logits(la, lb, strategy, raw_w, torch.tensor([1.7]))
+    kw = dict(strategy=code, w0=float(w[0]), w1=float(w[1]), temperature=1.7, auroc_bins=4096)
+    out = ops.score(la, lb, tgt, want_pred=torch.int64, want_fused=True, **kw)
+    assert torch.equal(out["pred"].cpu(), want.argmax(1))
+    got = out["fused"].cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(got, nan=0.0), torch.nan_to_num(want, nan=0.0))
+    # the bins-only kernel counts the same confusion matrix
+    fast = ops.read_bins(ops.score(la, lb, tgt, **kw)["bins"], 19, 15, 4096)
+    slow = ops.read_bins(out["bins"], 19, 15, 4096)
+    assert np.array_equal(fast.confusion, slow.confusion)
+    assert np.array_equal(fast.confusion, om.confusion_matrix(want, tgt, 19).numpy())
+
+
 def test_uint8_wrap_quirk_and_prediction_maps(pkg, golden):
     p, ops, _lib = pkg
     g = golden("metrics")
