@@ -93,6 +93,8 @@ _SIGNATURES = {
                               C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "awx_fogloss_workspace_bytes": (C.c_size_t, []),
+    "awx_fuse_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_float,
+                                   C.c_float, C.c_float, C.c_int32, C.c_void_p]),
     "awx_fuse_backward_workspace_bytes": (C.c_size_t, []),
     "awx_fuse_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
                                     C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -74,7 +74,7 @@ class EnsembleModel(nn.Module):
                                  self.ensemble_strategy)
         w0, w1, temp = self._fusion_scalars()
         code = _STRATEGY.get(self.ensemble_strategy, _lib.FUSE_MEAN)
-        return ops.score(seg1, seg2, strategy=code, w0=w0, w1=w1, temperature=temp, want_fused=True)["fused"]
+        return _fuse_forward(seg1, seg2, code, w0, w1, temp)
 
     def fuse_depth(self, d1: torch.Tensor, d2: torch.Tensor) -> torch.Tensor:
         """model.py:471-478: weighted for weighted_average, plain mean otherwise; no temperature."""
@@ -84,7 +84,7 @@ class EnsembleModel(nn.Module):
             return _FuseFn.apply(d1, d2, self.ensemble_weights, None, strategy)
         w0, w1, _ = self._fusion_scalars()
         code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
-        return ops.score(d1, d2, strategy=code, w0=w0, w1=w1, temperature=None, want_fused=True)["fused"]
+        return ops.fuse_forward(d1, d2, code, w0, w1, None)
 
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         o1 = self.segformer(x)
@@ -110,8 +110,17 @@ class EnsembleModel(nn.Module):
             return ops.score(o1["segmentation"], o2["segmentation"], strategy=_lib.FUSE_MEAN, want_js=True)["js"]
 
 
+def _fuse_forward(a, b, code, w0, w1, temp):
+    """The fused logits alone.  weighted_average / mean are element-wise (awx_fuse_forward, one streaming pass);
+    max_confidence needs both member softmaxes per pixel, which the TMA-staged score kernel already computes
+    faster than a plain per-pixel kernel does (its fused map, statistics discarded)."""
+    if code == _lib.FUSE_MAXCONF:
+        return ops.score(a, b, strategy=code, w0=w0, w1=w1, temperature=temp, want_fused=True)["fused"]
+    return ops.fuse_forward(a, b, code, w0, w1, temp)
+
+
 class _FuseFn(torch.autograd.Function):
-    """Differentiable fusion for training: forward through awx_score, backward through awx_fuse_backward (the two
+    """Differentiable fusion for training: forward through awx_fuse_forward, backward through awx_fuse_backward (the two
     scaled copies of the incoming gradient and the three dot products in one pass); only the 2-element softmax
     Jacobian of the raw weights and the temperature's scalar are formed from those sums afterwards."""
 
@@ -121,7 +130,7 @@ class _FuseFn(torch.autograd.Function):
         w0, w1 = float(w[0]), float(w[1])
         temp = None if temperature is None else float(temperature.detach().float().reshape(-1)[0])
         code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
-        fused = ops.score(a, b, strategy=code, w0=w0, w1=w1, temperature=temp, want_fused=True)["fused"]
+        fused = _fuse_forward(a, b, code, w0, w1, temp)
         ctx.save_for_backward(a, b)
         ctx.meta = (w0, w1, temp, code, raw_w, temperature)
         return fused

@@ -250,6 +250,23 @@ def members_n(members, labels: Optional[torch.Tensor] = None, *, ignore_index: i
     return out
 
 
+def fuse_forward(logits_a: torch.Tensor, logits_b: torch.Tensor, strategy: int, w0: float, w1: float,
+                 temperature: Optional[float]) -> torch.Tensor:
+    """awx_fuse_forward: the fused logits of two [B,C,H,W] members (EnsembleModel.forward), nothing else."""
+    lib = _lib.load()
+    a = to_device(logits_a, torch.float32)
+    b = to_device(logits_b, torch.float32)
+    if a.shape != b.shape or a.dim() != 4:
+        raise ValueError("fuse_forward needs two [B,C,H,W] tensors of equal shape")
+    bsz, ncls, h, w = a.shape
+    out = torch.empty_like(a)
+    rc = lib.awx_fuse_forward(_ptr(a), _ptr(b), _ptr(out), bsz, ncls, h * w, strategy, float(w0), float(w1),
+                              1.0 if temperature is None else float(temperature), 0 if temperature is None else 1,
+                              _stream())
+    _lib.check(rc, "awx_fuse_forward")
+    return out
+
+
 def fuse_backward(grad_fused: torch.Tensor, logits_a: torch.Tensor, logits_b: torch.Tensor, strategy: int, w0: float,
                   w1: float, temperature: Optional[float], want_a: bool = True, want_b: bool = True):
     """awx_fuse_backward: (grad_a | None, grad_b | None, dots fp64[3] device) for the fusion's backward pass."""

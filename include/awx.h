@@ -238,6 +238,15 @@ int awx_fogloss(const float* logits, const void* labels, int32_t label_dtype,
                 double* sums, float* dlogits, float* ddepth, float* dfog /*nullable*/,
                 int64_t* bad_labels, void* workspace, void* stream);
 
+/* EnsembleModel.forward's fused logits alone (models/model.py:443-462), without the statistics awx_score computes
+ * next to them -- what a training step wants: fused = (w0*a + w1*b | (a+b)/2 | a if max softmax(a) > max softmax(b)
+ * else b) [/ temperature].  Arithmetic as torch eager (the weighted sum rounds three times, max_confidence is
+ * mask*l1 + (1-mask)*l2, the division is a true division): equal to awx_score's fused map bit for bit.
+ * a, b, fused: device fp32 [batch, C, pixels_per_image] contiguous. */
+int awx_fuse_forward(const float* logits_a, const float* logits_b, float* fused, int64_t batch, int32_t num_classes,
+                     int64_t pixels_per_image, int32_t strategy, float w0, float w1, float temperature,
+                     int32_t use_temperature, void* stream);
+
 /* Gradient of EnsembleModel's fusion for training (models/model.py:442-462): with gs = grad_fused / T,
  * grad_a = gs*w0 | gs/2 | gs*[member a picked], grad_b likewise (either may be NULL), and
  * dots (device fp64 [3], overwritten) = {sum gs*a, sum gs*b, sum grad_fused*fused}, from which the caller forms the

@@ -207,6 +207,35 @@ def test_ties_nan_and_degenerate(pkg):
 
 
 @pytest.mark.parametrize("strategy", ["weighted_average", "max_confidence", "mean"])
+@pytest.mark.parametrize("temp", [None, 1.7, 0.37])
+def test_fuse_forward_bit_exact(pkg, strategy, temp):
+    """awx_fuse_forward (EnsembleModel.forward's tensor, no statistics) == the reference's fusion expression ==
+    awx_score's fused map, on vector-friendly and odd shapes and on a depth-head shaped [B,1,H,W] pair."""
+    p, ops, _lib = pkg
+    raw_w = torch.tensor([0.3, 0.9])
+    w = of_.member_weights(raw_w)
+    code = {"weighted_average": _lib.FUSE_WEIGHTED, "max_confidence": _lib.FUSE_MAXCONF, "mean": _lib.FUSE_MEAN}[strategy]
+    tt = None if temp is None else torch.tensor([temp])
+    for seed, (b, c, h, w_) in enumerate([(2, 19, 48, 64), (1, 19, 7, 9), (3, 5, 5, 3), (2, 1, 33, 20)]):
+        if c == 1 and strategy == "max_confidence":
+            continue   # the depth heads are fused by the weighted / mean expressions only (model.py:471-478)
+        gen = torch.Generator().manual_seed(40 + seed)
+        la = torch.randn(b, c, h, w_, generator=gen) * 3
+        lb = torch.randn(b, c, h, w_, generator=gen) * 3
+        want = of_.fuse_logits(la, lb, strategy, raw_w, tt)
+        got = ops.fuse_forward(la, lb, code, float(w[0]), float(w[1]), temp)
+        assert got.is_cuda and torch.equal(got.cpu(), want), (strategy, temp, (b, c, h, w_))
+        via_score = ops.score(la, lb, strategy=code, w0=float(w[0]), w1=float(w[1]), temperature=temp, want_fused=True)["fused"]
+        assert torch.equal(got, via_score)
+    # unaligned views take the scalar path
+    la = torch.randn(1, 19, 8, 33, generator=torch.Generator().manual_seed(1)).cuda()
+    lb = torch.randn(1, 19, 8, 33, generator=torch.Generator().manual_seed(2)).cuda()
+    a_off, b_off = la.flatten()[1:].reshape(-1)[:19 * 8 * 32].view(1, 19, 8, 32), lb.flatten()[3:][:19 * 8 * 32].view(1, 19, 8, 32)
+    want = of_.fuse_logits(a_off.cpu(), b_off.cpu(), strategy, raw_w, tt)
+    assert torch.equal(ops.fuse_forward(a_off, b_off, code, float(w[0]), float(w[1]), temp).cpu(), want)
+
+
+@pytest.mark.parametrize("strategy", ["weighted_average", "max_confidence", "mean"])
 def test_ensemble_non_finite_logits_follow_the_reference(pkg, strategy):
     """+-inf / NaN logits in either member: the prediction map is the arg-max of the reference's own fusion
     expression (0 * inf = NaN in max_confidence's `mask*l1 + (1-mask)*l2` included; NaN wins torch's arg-max),
