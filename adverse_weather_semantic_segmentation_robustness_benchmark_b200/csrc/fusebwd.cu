@@ -104,6 +104,78 @@ __global__ void __launch_bounds__(kFThreads) fuse_forward_maxconf_kernel(const f
   }
 }
 
+// fp64 partial sums: thread -> warp (shuffles) -> CTA (shared memory) -> part[3 * blockIdx.x + k]
+__device__ __forceinline__ void block_reduce3(double da, double db, double du, double* __restrict__ part) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    da += __shfl_down_sync(0xffffffffu, da, o);
+    db += __shfl_down_sync(0xffffffffu, db, o);
+    du += __shfl_down_sync(0xffffffffu, du, o);
+  }
+  __shared__ double s[3][kFThreads / 32];
+  if ((threadIdx.x & 31) == 0) {
+    s[0][threadIdx.x >> 5] = da;
+    s[1][threadIdx.x >> 5] = db;
+    s[2][threadIdx.x >> 5] = du;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < kFThreads / 32; ++w) t += s[threadIdx.x][w];
+    part[3 * blockIdx.x + threadIdx.x] = t;
+  }
+}
+
+// weighted_average / mean: the gradient is element-wise too (constant ka, kb): 16-byte vectors over the flat
+// tensors, two vectors of each input in flight per thread; the three dot products ride along in fp64.
+__global__ void __launch_bounds__(kFThreads) fuse_backward_flat_kernel(const float* __restrict__ g, const float* __restrict__ a,
+                                                                        const float* __restrict__ b, float* __restrict__ ga,
+                                                                        float* __restrict__ gb, long long n, float ka, float kb,
+                                                                        float inv_t, double* __restrict__ part, int vec) {
+  const long long stride = (long long)gridDim.x * kFThreads, t0 = (long long)blockIdx.x * kFThreads + threadIdx.x;
+  double da = 0.0, db = 0.0, du = 0.0;
+  auto elem = [&](float gv, float va, float vb, float& xa, float& xb) {
+    const float gs = gv * inv_t;
+    xa = gs * ka;
+    xb = gs * kb;
+    da += (double)gs * (double)va;
+    db += (double)gs * (double)vb;
+    du += (double)xa * (double)va + (double)xb * (double)vb;
+  };
+  auto vec4 = [&](const float4& gv, const float4& va, const float4& vb, long long i) {
+    float4 xa, xb;
+    elem(gv.x, va.x, vb.x, xa.x, xb.x);
+    elem(gv.y, va.y, vb.y, xa.y, xb.y);
+    elem(gv.z, va.z, vb.z, xa.z, xb.z);
+    elem(gv.w, va.w, vb.w, xa.w, xb.w);
+    if (ga) __stcs(reinterpret_cast<float4*>(ga) + i, xa);
+    if (gb) __stcs(reinterpret_cast<float4*>(gb) + i, xb);
+  };
+  long long tail0 = 0;
+  if (vec) {
+    const long long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    long long i = t0;
+    for (; i + stride < n4; i += 2 * stride) {
+      const float4 g0 = __ldcs(g4 + i), a0 = __ldcs(a4 + i), b0 = __ldcs(b4 + i);
+      const float4 g1 = __ldcs(g4 + i + stride), a1 = __ldcs(a4 + i + stride), b1 = __ldcs(b4 + i + stride);
+      vec4(g0, a0, b0, i);
+      vec4(g1, a1, b1, i + stride);
+    }
+    for (; i < n4; i += stride) vec4(__ldcs(g4 + i), __ldcs(a4 + i), __ldcs(b4 + i), i);
+    tail0 = n4 << 2;
+  }
+  for (long long i = tail0 + t0; i < n; i += stride) {
+    float xa, xb;
+    elem(g[i], a[i], b[i], xa, xb);
+    if (ga) ga[i] = xa;
+    if (gb) gb[i] = xb;
+  }
+  block_reduce3(da, db, du, part);
+}
+
 __global__ void __launch_bounds__(kFThreads) fuse_backward_kernel(const float* __restrict__ g, const float* __restrict__ a,
                                                                    const float* __restrict__ b, float* __restrict__ ga,
                                                                    float* __restrict__ gb, long long B, int C, long long HW,
@@ -135,24 +207,7 @@ __global__ void __launch_bounds__(kFThreads) fuse_backward_kernel(const float* _
       du += (double)xa * (double)va + (double)xb * (double)vb;
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    da += __shfl_down_sync(0xffffffffu, da, o);
-    db += __shfl_down_sync(0xffffffffu, db, o);
-    du += __shfl_down_sync(0xffffffffu, du, o);
-  }
-  __shared__ double s[3][kFThreads / 32];
-  if ((threadIdx.x & 31) == 0) {
-    s[0][threadIdx.x >> 5] = da;
-    s[1][threadIdx.x >> 5] = db;
-    s[2][threadIdx.x >> 5] = du;
-  }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    double t = 0.0;
-    for (int w = 0; w < kFThreads / 32; ++w) t += s[threadIdx.x][w];
-    part[3 * blockIdx.x + threadIdx.x] = t;
-  }
+  block_reduce3(da, db, du, part);
 }
 
 __global__ void fuse_backward_finish_kernel(const double* __restrict__ part, int n, double* __restrict__ dots) {
@@ -218,8 +273,17 @@ extern "C" int awx_fuse_backward(const float* grad_fused, const float* logits_a,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   double* part = static_cast<double*>(workspace);
   const float inv_t = use_temperature ? 1.0f / temperature : 1.0f;
-  fuse_backward_kernel<<<(unsigned)blocks, kFThreads, 0, s>>>(grad_fused, logits_a, logits_b, grad_a, grad_b, batch, C,
-                                                              pixels_per_image, strategy, w0, w1, inv_t, part);
+  if (strategy == AWX_FUSE_MAXCONF) {
+    fuse_backward_kernel<<<(unsigned)blocks, kFThreads, 0, s>>>(grad_fused, logits_a, logits_b, grad_a, grad_b, batch, C,
+                                                                pixels_per_image, strategy, w0, w1, inv_t, part);
+  } else {
+    const long long n = total * C;
+    const int vec = (((uintptr_t)grad_fused | (uintptr_t)logits_a | (uintptr_t)logits_b | (uintptr_t)grad_a |
+                      (uintptr_t)grad_b) & 15) == 0;
+    const bool mean = strategy == AWX_FUSE_MEAN;
+    fuse_backward_flat_kernel<<<(unsigned)blocks, kFThreads, 0, s>>>(grad_fused, logits_a, logits_b, grad_a, grad_b, n,
+                                                                     mean ? 0.5f : w0, mean ? 0.5f : w1, inv_t, part, vec);
+  }
   fuse_backward_finish_kernel<<<1, 32, 0, s>>>(part, (int)blocks, dots);
   AWX_CUDA(cudaGetLastError());
   note_launch(2);

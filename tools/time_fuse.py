@@ -32,3 +32,16 @@ for _ in range(10):
     e0.record(); torch.add(la, lb, out=out); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print(f"torch.add(la, lb)          {st.median(ts):7.3f} ms  {px*228/st.median(ts)/1e6:8.1f} GB/s")
+g = torch.randn_like(la)
+for name, code, temp in (("weighted T=1.7", _lib.FUSE_WEIGHTED, 1.7), ("mean no T", _lib.FUSE_MEAN, None), ("max_confidence T=1", _lib.FUSE_MAXCONF, 1.0)):
+    fn = lambda: ops.fuse_backward(g, la, lb, code, 0.35, 0.65, temp)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = st.median(ts)
+    print(f"awx_fuse_backward      {name:20s} {ms:7.3f} ms  {px*380/ms/1e6:8.1f} GB/s (380 B/px)", flush=True)
