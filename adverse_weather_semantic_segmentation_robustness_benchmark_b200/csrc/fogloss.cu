@@ -6,11 +6,17 @@
 //   ddepth[i]    = 2 * (depth_pred_i - depth_tgt_i) / N
 //   dfog[i]      = s * base_loss_i / N     (needed when fog density itself depends on the depth head)
 // (FogDensityAwareLoss.forward, models/model.py:577-611; autograd of the same expressions).
-// Layout and load pattern as in score.cu: a thread owns PX consecutive pixels, 64-bit loads per
-// class plane, everything in registers; gradients are stored with the same pattern.
+// Two kernels.  fogloss_kernel (any C, any alignment): load pattern as in score.cu, a thread owns PX consecutive
+// pixels, 64-bit loads per class plane, everything in registers; gradients are stored with the same pattern.
+// fogloss_ring_kernel (C == 19, 16-byte aligned planes): the score kernel's TMA ring -- one persistent CTA per SM,
+// a producer warp streams 608-pixel tiles of the 19 planes into shared memory with bulk async copies while 19
+// consumer warps (one pixel per thread) work on the tiles that have landed, so HBM reads never wait for the
+// arithmetic or for the gradient stores (the register kernel is latency bound: 16 warps per SM, every load phase
+// exposed).  Same per-pixel arithmetic in both.
 // Sums: fp64 per thread -> warp shuffle -> CTA -> one partial per CTA, reduced in CTA order by a
 // second single-block kernel, so the result is bit-reproducible for a given device.
 #include "awx_internal.cuh"
+#include "tma_ring.cuh"
 
 namespace awx {
 namespace {
@@ -182,6 +188,188 @@ int launch_loss(LossParams& p, double* sums, cudaStream_t s) {
   return AWX_OK;
 }
 
+// ------------------------------------------------------------------------------------------- TMA-staged kernel
+constexpr int kRC = 19;                           // classes
+constexpr int kRingWarps = 19;                    // consumer warps
+constexpr int kRingTile = 32 * kRingWarps;        // pixels per tile
+constexpr int kRingThreads = kRingTile + 32;      // + producer warp
+constexpr int kRingUnits = 4;                     // ring depth (tiles)
+constexpr int kRingUnitBytes = kRC * kRingTile * 4;
+constexpr size_t kRingSmem = 128 + (size_t)kRingUnits * kRingUnitBytes;  // [full[4] | empty[4] | pad | units]
+
+__global__ void __launch_bounds__(kRingThreads, 1) fogloss_ring_kernel(const __grid_constant__ LossParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  u64* full = reinterpret_cast<u64*>(smem);
+  u64* empty = full + kRingUnits;
+  float* units = reinterpret_cast<float*>(smem + 128);
+  if (threadIdx.x == 0) {
+    for (int u = 0; u < kRingUnits; ++u) {
+      mbar_init(full + u, 1);
+      mbar_init(empty + u, kRingWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const long long HW = p.HW;
+  const long long tpi = (HW + kRingTile - 1) / kRingTile;  // tiles per image
+  const long long ntiles = p.B * tpi;
+  double acc_seg = 0.0, acc_depth = 0.0;
+  unsigned n_bad = 0;
+
+  if (threadIdx.x >= kRingTile) {
+    // ------------------------------------------------------------------ producer warp
+    unsigned u = 0, ph = 0;
+    long long img = blockIdx.x / tpi, tin = blockIdx.x - img * tpi;  // image and tile-in-image, advanced incrementally
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long p0 = tin * kRingTile;
+      const unsigned npx = (unsigned)((HW - p0) < kRingTile ? (HW - p0) : kRingTile);
+      mbar_wait(empty + u, ph ^ 1u);
+      if (elect_one()) {  // one thread, warp-uniform operands: the copies stay on the uniform datapath
+        mbar_expect_tx(full + u, kRC * npx * 4u);
+        const float* src = p.logits + img * kRC * HW + p0;
+        float* dst = units + (size_t)u * (kRC * kRingTile);
+#pragma unroll
+        for (int c = 0; c < kRC; ++c) bulk_load(dst + c * kRingTile, src + c * HW, npx * 4u, full + u);
+      }
+      __syncwarp();
+      if (++u == (unsigned)kRingUnits) {
+        u = 0;
+        ph ^= 1u;
+      }
+      tin += gridDim.x;
+      while (tin >= tpi) {
+        tin -= tpi;
+        ++img;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ consumer warps: thread t owns pixel t
+    const int t = threadIdx.x, lane = t & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t my0 = sbase + 128u + 4u * (uint32_t)t;
+    unsigned u = 0, ph = 0;
+    long long img_next = blockIdx.x / tpi, tin_next = blockIdx.x - img_next * tpi;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long img = img_next, p0 = tin_next * kRingTile;
+      tin_next += gridDim.x;
+      while (tin_next >= tpi) {
+        tin_next -= tpi;
+        ++img_next;
+      }
+      const bool act = p0 + t < HW;  // false only in the tail tile of an image (stale ring contents, nothing stored)
+      const long long li = img * HW + p0 + t;
+      // side inputs first: their latency overlaps the wait for the tile
+      long long y = 0;
+      float fogv = 0.f, dp = 0.f, dt = 0.f;
+      if (act) {
+        y = p.label_mode == AWX_LABEL_U8 ? (long long)static_cast<const uint8_t*>(p.labels)[li]
+                                         : static_cast<const long long*>(p.labels)[li];
+        if (p.fog) fogv = p.fog[li];
+        if (p.dpred && p.dtgt) {
+          dp = p.dpred[li];
+          dt = p.dtgt[li];
+        }
+      }
+      float x[kRC];
+      mbar_wait_a(sbase + 8u * u, ph);
+      const uint32_t s0 = my0 + u * (uint32_t)kRingUnitBytes;
+#pragma unroll
+      for (int c = 0; c < kRC; ++c) x[c] = lds_f32(s0 + c * kRingTile * 4);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(sbase + 8u * (kRingUnits + u));
+      if (++u == (unsigned)kRingUnits) {
+        u = 0;
+        ph ^= 1u;
+      }
+      if (!act) continue;
+      // ---- the per-pixel arithmetic of fogloss_kernel, unchanged
+      const bool ok = y >= 0 && y < kRC;
+      n_bad += !ok;
+      float mx = x[0];
+#pragma unroll
+      for (int c = 1; c < kRC; ++c) mx = fmaxf(mx, x[c]);
+      float sum = 0.f, xy = 0.f;
+#pragma unroll
+      for (int c = 0; c < kRC; ++c) {
+        const float d = x[c] - mx;
+        if (c == (int)y) xy = d;
+        const float e = ex2_approx(d * kLog2e);
+        sum += e;
+        x[c] = e;
+      }
+      const float ce = kLn2 * lg2_approx(sum) - xy;
+      float w = 1.0f;
+      if (p.fog) w = fmaf(p.sens, fogv, 1.0f);
+      float lossv = ce, gscale = 1.0f;
+      if (p.focal) {
+        const float pt = ex2_approx(-ce * kLog2e);
+        const float om = 1.0f - pt;
+        lossv = om * om * ce;
+        gscale = om * om + 2.0f * om * pt * ce;
+      }
+      if (ok) acc_seg += (double)(lossv * w);
+      if (p.dfog) p.dfog[li] = ok ? p.sens * lossv * p.inv_n : 0.f;
+      if (p.dlogits) {
+        const float k = ok ? w * gscale * p.inv_n : 0.f;
+        const float r = __frcp_rn(sum);
+        float* go = p.dlogits + img * kRC * HW + p0 + t;
+#pragma unroll
+        for (int c = 0; c < kRC; ++c) {
+          const float prob = x[c] * r;
+          __stcs(go + c * HW, k * (prob - (c == (int)y ? 1.0f : 0.0f)));
+        }
+      }
+      if (p.dpred && p.dtgt) {
+        const float diff = dp - dt;
+        acc_depth += (double)(diff * diff);
+        if (p.ddepth) p.ddepth[li] = 2.0f * diff * p.inv_n;
+      }
+    }
+  }
+  // ---- CTA reduction (fixed order) -> one partial per CTA; the producer warp contributes zeros
+  __shared__ double s_red[2][kRingThreads / 32];
+  __shared__ unsigned s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc_seg += __shfl_down_sync(0xffffffffu, acc_seg, o);
+    acc_depth += __shfl_down_sync(0xffffffffu, acc_depth, o);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    s_red[0][threadIdx.x >> 5] = acc_seg;
+    s_red[1][threadIdx.x >> 5] = acc_depth;
+  }
+  const unsigned wb = __reduce_add_sync(0xffffffffu, n_bad);
+  if ((threadIdx.x & 31) == 0 && wb) atomicAdd(&s_bad, wb);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, d = 0.0;
+    for (int w = 0; w < kRingThreads / 32; ++w) {
+      a += s_red[0][w];
+      d += s_red[1][w];
+    }
+    p.partials[2 * blockIdx.x] = a;
+    p.partials[2 * blockIdx.x + 1] = d;
+    if (s_bad && p.bad) atomicAdd(p.bad, (unsigned long long)s_bad);
+  }
+}
+
+int launch_loss_ring(LossParams& p, double* sums, cudaStream_t s) {
+  AWX_CUDA(cudaFuncSetAttribute(fogloss_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem));
+  const long long ntiles = p.B * ((p.HW + kRingTile - 1) / kRingTile);
+  long long blocks = sm_count();
+  if (blocks > ntiles) blocks = ntiles;
+  fogloss_ring_kernel<<<(unsigned)blocks, kRingThreads, kRingSmem, s>>>(p);
+  AWX_CUDA(cudaGetLastError());
+  note_launch();
+  fogloss_finish_kernel<<<1, 32, 0, s>>>(p.partials, (int)blocks, sums);
+  AWX_CUDA(cudaGetLastError());
+  note_launch();
+  return AWX_OK;
+}
+
 __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ scale) {
   const float k = *scale;
   const long long n4 = n / 4;
@@ -236,6 +424,13 @@ extern "C" int awx_fogloss(const float* logits, const void* labels, int32_t labe
   p.bad = reinterpret_cast<unsigned long long*>(bad_labels);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec2 = (pixels_per_image % 2 == 0) && ((uintptr_t)logits & 7) == 0 && ((uintptr_t)dlogits & 7) == 0;
+  // TMA ring whenever the bulk copies' alignment rules hold (AWX_LOSS_KERNEL=v1 forces the register kernel: A/B
+  // measurements and parity tests of both)
+  static const bool force_v1 = [] {
+    const char* e = getenv("AWX_LOSS_KERNEL");
+    return e && e[0] == 'v' && e[1] == '1';
+  }();
+  if (C == 19 && !force_v1 && pixels_per_image % 4 == 0 && ((uintptr_t)logits & 15) == 0) return launch_loss_ring(p, sums, s);
   if (C == 19) return vec2 ? launch_loss<19, 2>(p, sums, s) : launch_loss<19, 1>(p, sums, s);
   return launch_loss<0, 1>(p, sums, s);
 }

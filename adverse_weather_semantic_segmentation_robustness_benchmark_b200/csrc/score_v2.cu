@@ -19,6 +19,7 @@
 // 64-bit before they can overflow).  Pixels with non-finite sums (NaN / inf logits) and pixels
 // within 16 ulp of an ECE edge take the scalar slow paths shared with kernel v1.
 #include "score_common.cuh"
+#include "tma_ring.cuh"
 
 namespace awx {
 using namespace score_detail;
@@ -44,59 +45,6 @@ constexpr int kFastEceBins = 15, kFastAurocBins = 4096;  // the streaming evalua
 constexpr int kSingleWarps = 19;                // consumer warps of the bins-only single-member kernels
 constexpr unsigned kFlushPixels = 60000;        // per-warp confidence sums are flushed before 2^16 pixels
 constexpr int kEceRep = 16;                     // replicas (lane & 15) of the per-warp confidence-sum words
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// true for exactly one (the first active) lane of a converged warp: the pattern ptxas recognises to keep the
-// operands of the elected thread's instructions in uniform registers
-__device__ __forceinline__ bool elect_one() {
-  unsigned pred = 0;
-  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n @p mov.u32 %0, 1;\n}" : "+r"(pred));
-  return pred != 0;
-}
-// the same operations on 32-bit shared addresses (the hot loops keep one shared base register and add
-// immediates; converting a generic pointer costs an S2R + LEA every time)
-__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns): park instead of spinning
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsigned bytes, u64* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // shared-memory reduction on a 32-bit shared address (no generic -> shared conversion at the use site)
 __device__ __forceinline__ void red_add(uint32_t addr, unsigned v) {
