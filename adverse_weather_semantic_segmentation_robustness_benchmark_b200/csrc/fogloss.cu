@@ -190,10 +190,16 @@ int launch_loss(LossParams& p, double* sums, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------- TMA-staged kernel
 constexpr int kRC = 19;                           // classes
-constexpr int kRingWarps = 19;                    // consumer warps
+#ifndef AWX_LOSS_RING_WARPS
+#define AWX_LOSS_RING_WARPS 19
+#endif
+#ifndef AWX_LOSS_RING_UNITS
+#define AWX_LOSS_RING_UNITS 4
+#endif
+constexpr int kRingWarps = AWX_LOSS_RING_WARPS;   // consumer warps
 constexpr int kRingTile = 32 * kRingWarps;        // pixels per tile
 constexpr int kRingThreads = kRingTile + 32;      // + producer warp
-constexpr int kRingUnits = 4;                     // ring depth (tiles)
+constexpr int kRingUnits = AWX_LOSS_RING_UNITS;   // ring depth (tiles)
 constexpr int kRingUnitBytes = kRC * kRingTile * 4;
 constexpr size_t kRingSmem = 128 + (size_t)kRingUnits * kRingUnitBytes;  // [full[4] | empty[4] | pad | units]
 
@@ -426,10 +432,8 @@ extern "C" int awx_fogloss(const float* logits, const void* labels, int32_t labe
   const bool vec2 = (pixels_per_image % 2 == 0) && ((uintptr_t)logits & 7) == 0 && ((uintptr_t)dlogits & 7) == 0;
   // TMA ring whenever the bulk copies' alignment rules hold (AWX_LOSS_KERNEL=v1 forces the register kernel: A/B
   // measurements and parity tests of both)
-  static const bool force_v1 = [] {
-    const char* e = getenv("AWX_LOSS_KERNEL");
-    return e && e[0] == 'v' && e[1] == '1';
-  }();
+  const char* force = getenv("AWX_LOSS_KERNEL");
+  const bool force_v1 = force && force[0] == 'v' && force[1] == '1';
   if (C == 19 && !force_v1 && pixels_per_image % 4 == 0 && ((uintptr_t)logits & 15) == 0) return launch_loss_ring(p, sums, s);
   if (C == 19) return vec2 ? launch_loss<19, 2>(p, sums, s) : launch_loss<19, 1>(p, sums, s);
   return launch_loss<0, 1>(p, sums, s);

@@ -242,3 +242,36 @@ def test_fusion_backward_kernel(pkg, strategy, ts):
         _close(ens.ensemble_weights.grad.cpu().numpy(), rw.grad.numpy(), 1e-4, 1e-5)
     if ts:
         _close(ens.temperature.grad.cpu().numpy(), t.grad.numpy(), 1e-4, 1e-5)
+
+
+def test_ring_kernel_matches_register_kernel(monkeypatch):
+    """awx_fogloss's TMA-staged kernel (C = 19, aligned planes) against the register kernel (AWX_LOSS_KERNEL=v1) on
+    frames with a tail tile per image (H*W = 1 200 is not a multiple of the 608-pixel tile), labels of both dtypes
+    and an out-of-range label: same sums, same gradients, same bad-label count."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops_loss
+    gen = torch.Generator().manual_seed(3)
+    b, c, h, w = 3, 19, 30, 40
+    logits = (torch.randn(b, c, h, w, generator=gen) * 3).cuda()
+    fog = torch.rand(b, h, w, generator=gen).cuda()
+    dp, dt = (torch.rand(b, h, w, generator=gen) * 40).cuda(), (torch.rand(b, h, w, generator=gen) * 40).cuda()
+    for dtype in (torch.int64, torch.uint8):
+        labels = torch.randint(0, c, (b, h, w), generator=gen).to(dtype).cuda()
+        labels[1, 2, 3] = 200
+        for focal in (False, True):
+            outs = {}
+            for kern in ("ring", "v1"):
+                if kern == "v1":
+                    monkeypatch.setenv("AWX_LOSS_KERNEL", "v1")
+                else:
+                    monkeypatch.delenv("AWX_LOSS_KERNEL", raising=False)
+                outs[kern] = ops_loss.fogloss_raw(logits, labels, fog, dp, dt, 2.0, focal, True, True)
+            ring, v1 = outs["ring"], outs["v1"]
+            assert len(ring) == len(v1)
+            for a, r in zip(ring, v1):
+                if isinstance(a, torch.Tensor):
+                    if a.dtype.is_floating_point:
+                        torch.testing.assert_close(a, r, rtol=1e-6, atol=1e-12)
+                    else:
+                        assert torch.equal(a, r)
+                else:
+                    assert a == r
