@@ -26,7 +26,9 @@ CLEAN, FOG, RAIN, SNOW, NIGHT = 0, 1, 2, 3, 4
 F32, F64, BF16, U8 = 0, 1, 2, 3
 KIND_CODES = {"clean": CLEAN, "fog": FOG, "rain": RAIN, "snow": SNOW, "night": NIGHT}
 
-CNT_VALID, CNT_CORRECT, CNT_BAD_LABEL, CNT_ECE_AMBIG, CNT_ENS_WRONG, CNT_PICK_AMBIG, CNT_NO_BIN, CNT_PIXELS = range(8)
+NUM_COUNTERS = 16
+(CNT_VALID, CNT_CORRECT, CNT_BAD_LABEL, CNT_ECE_AMBIG, CNT_ENS_WRONG, CNT_PICK_AMBIG, CNT_NO_BIN, CNT_PIXELS,
+ CNT_MARG_AMBIG, CNT_EPRED_AMBIG) = range(10)
 
 
 class ScoreConfig(C.Structure):

@@ -27,10 +27,62 @@ struct MembersParams {
   float scale, top;
   unsigned long long* pos;   // [NB]
   unsigned long long* neg;   // [NB]
-  unsigned long long* counters;  // AWX_CNT_* [8]
+  unsigned long long* counters;  // AWX_CNT_* [AWX_NUM_COUNTERS]
   float* mi;
   float* var;
 };
+
+// Rare path: arg-max of the mean member probabilities for a pixel whose two best classes the fp32 loop cannot
+// separate (within 4e-6 relative).  fp64 softmaxes; classes within 8e-7 of the fp64 maximum are candidates;
+// identical member logits tie for certain (first index); otherwise the fp32 mean of the fp32-rounded
+// probabilities (torch: stack(...).mean(0), metrics.py:414-416) decides and, when the label is a candidate, the
+// pixel is counted as ambiguous (AWX_CNT_MARG_AMBIG).  Same rule as resolve_ties (score_common.cuh).
+static __device__ __noinline__ int resolve_marg_n(const MembersParams& p, int C, long long img, long long px, long long lab,
+                                                  int* ambig) {
+  double mean[AWX_MAX_CLASSES];
+  for (int c = 0; c < C; ++c) mean[c] = 0.0;
+  for (int k = 0; k < p.n; ++k) {
+    const float* g = p.m[k] + img * C * p.HW + px;
+    float mx = g[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, g[(long long)c * p.HW]);
+    double s = 0.0;
+    for (int c = 0; c < C; ++c) s += exp((double)__fsub_rn(g[(long long)c * p.HW], mx));
+    for (int c = 0; c < C; ++c) mean[c] += exp((double)__fsub_rn(g[(long long)c * p.HW], mx)) / s;
+  }
+  int arg = 0;
+  for (int c = 1; c < C; ++c)
+    if (mean[c] > mean[arg]) arg = c;
+  const double thr = mean[arg] * (1.0 - 8e-7);
+  int ncand = 0, nsame = 0, lab_in = 0, first = -1, best = arg;
+  float mbest = -1.f;
+  for (int c = 0; c < C; ++c) {
+    if (!(mean[c] >= thr)) continue;
+    if (first < 0) first = c;
+    ++ncand;
+    lab_in |= (long long)c == lab;
+    bool same = true;
+    float acc = 0.f;
+    for (int k = 0; k < p.n; ++k) {
+      const float* g = p.m[k] + img * C * p.HW + px;
+      same = same && g[(long long)c * p.HW] == g[(long long)first * p.HW];
+      float mx = g[0];
+      for (int j = 1; j < C; ++j) mx = fmaxf(mx, g[(long long)j * p.HW]);
+      double s = 0.0;
+      for (int j = 0; j < C; ++j) s += exp((double)__fsub_rn(g[(long long)j * p.HW], mx));
+      acc = __fadd_rn(acc, (float)(exp((double)__fsub_rn(g[(long long)c * p.HW], mx)) / s));
+    }
+    nsame += same;
+    const float m32 = __fdiv_rn(acc, (float)p.n);
+    if (m32 > mbest) {
+      mbest = m32;
+      best = c;
+    }
+  }
+  if (ncand <= 1) return arg;
+  if (nsame == ncand) return first;
+  *ambig = lab_in;
+  return best;
+}
 
 template <int CS>
 __global__ void __launch_bounds__(256) members_kernel(const __grid_constant__ MembersParams p) {
@@ -38,7 +90,7 @@ __global__ void __launch_bounds__(256) members_kernel(const __grid_constant__ Me
   const int C = CS > 0 ? CS : p.C;
   const long long total = p.B * p.HW;
   const float inv_n = __fdiv_rn(1.0f, (float)p.n);
-  unsigned n_valid = 0, n_wrong = 0;
+  unsigned n_valid = 0, n_wrong = 0, n_mamb = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long img = i / p.HW, px = i - img * p.HW;
     float mean[CA];
@@ -70,17 +122,21 @@ __global__ void __launch_bounds__(256) members_kernel(const __grid_constant__ Me
       }
       h_each += h;
     }
-    float hm = 0.f, best = -1.f;
+    float hm = 0.f, best = -1.f, second = -1.f;
     int arg = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       mean[c] *= inv_n;
       hm = fmaf(mean[c], lg2_approx(mean[c] + kEpsM), hm);
       if (mean[c] > best) {
+        second = best;
         best = mean[c];
         arg = c;
+      } else {
+        second = fmaxf(second, mean[c]);
       }
     }
+    const bool tie = C > 1 && second >= best * (1.f - 4e-6f);
     const float mi = kLn2 * (h_each * inv_n - hm);  // H(mean) - mean_k H_k with H = -sum p ln(p+eps)
     if (p.mi) p.mi[i] = mi;
     if (p.var) {
@@ -123,6 +179,11 @@ __global__ void __launch_bounds__(256) members_kernel(const __grid_constant__ Me
         y = static_cast<const long long*>(p.labels)[i];
       if (y != p.ignore_index) {
         ++n_valid;
+        if (tie) {
+          int amb = 0;
+          arg = resolve_marg_n(p, C, img, px, y, &amb);
+          n_mamb += amb;
+        }
         const bool wrong = y != arg;
         n_wrong += wrong;
         if (p.NB > 0) {
@@ -135,9 +196,11 @@ __global__ void __launch_bounds__(256) members_kernel(const __grid_constant__ Me
   }
   if (p.labels) {
     const unsigned v = __reduce_add_sync(0xffffffffu, n_valid), w = __reduce_add_sync(0xffffffffu, n_wrong);
+    const unsigned m = __reduce_add_sync(0xffffffffu, n_mamb);
     if ((threadIdx.x & 31) == 0) {
       if (v) atomicAdd(p.counters + AWX_CNT_VALID, (unsigned long long)v);
       if (w) atomicAdd(p.counters + AWX_CNT_ENS_WRONG, (unsigned long long)w);
+      if (m) atomicAdd(p.counters + AWX_CNT_MARG_AMBIG, (unsigned long long)m);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.counters + AWX_CNT_PIXELS, (unsigned long long)total);
   }

@@ -43,10 +43,10 @@ __global__ void __launch_bounds__(kThreads, CS > 0 ? 2 : 1) score_kernel(const _
   unsigned* s_ece_cor = s_ece_cnt + kWarps * nb;                                          // [kWarps][nb]
   unsigned* s_conf = s_ece_cor + kWarps * nb;                                             // [C*C]
   unsigned* s_auroc = s_conf + C * C;                                                     // [2*NB]
-  unsigned* s_cnt = s_auroc + 2 * NB;                                                     // [8]
-  float* s_edges = reinterpret_cast<float*>(s_cnt + 8);                                   // [nb+1]
+  unsigned* s_cnt = s_auroc + 2 * NB;                                                     // [AWX_NUM_COUNTERS]
+  float* s_edges = reinterpret_cast<float*>(s_cnt + AWX_NUM_COUNTERS);                                   // [nb+1]
   {
-    const int words = kWarps * nb * 4 + C * C + 2 * NB + 8;  // u64 counts as two words
+    const int words = kWarps * nb * 4 + C * C + 2 * NB + AWX_NUM_COUNTERS;  // u64 counts as two words
     unsigned* w = reinterpret_cast<unsigned*>(smem);
     for (int i = threadIdx.x; i < words; i += kThreads) w[i] = 0u;
     for (int i = threadIdx.x; i <= nb; i += kThreads) s_edges[i] = p.edges[i];
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kThreads, CS > 0 ? 2 : 1) score_kernel(const _
   const long long stride = (long long)gridDim.x * kThreads;
   const bool mean = ENS && p.strategy == AWX_FUSE_MEAN;
   unsigned n_valid = 0, n_correct = 0, n_bad = 0, n_ambig = 0, n_wrong = 0, n_pick = 0, n_nobin = 0, n_pix = 0;
+  unsigned n_mamb = 0, n_eamb = 0;
 
   for (long long g0 = (long long)blockIdx.x * kThreads + warp * 32; g0 < total; g0 += stride) {
     const long long g = g0 + lane;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, CS > 0 ? 2 : 1) score_kernel(const _
       o[j].mi = 0.f;
       o[j].js = 0.f;
       o[j].mpred = 0;
-      score_pixel<CS, ENS, JS>(a[j], b[j], C, p, s_edges, ga + j, ENS ? gb + j : nullptr, w0, w1, amax, bmax, o[j]);
+      score_pixel<CS, ENS, JS>(a[j], b[j], C, p, s_edges, ga + j, ENS ? gb + j : nullptr, w0, w1, amax, bmax, lab[j], o[j]);
       if (act) n_pick += pick_ambig;
     }
 
@@ -176,10 +177,12 @@ __global__ void __launch_bounds__(kThreads, CS > 0 ? 2 : 1) score_kernel(const _
         const long long t = lab[j];
         const bool valid = act && t != (long long)p.ignore_index;
         const int pred = o[j].pred;
-        const bool correct = valid && t == (long long)pred;
+        // the ECE's accuracy term compares the arg-max of the PROBABILITIES (metrics.py:161-170); pixel accuracy
+        // and the confusion matrix use the arg-max of the logits
+        const bool correct = valid && t == (long long)o[j].epred;
         n_pix += act;
         n_valid += valid;
-        n_correct += correct;
+        n_correct += valid && t == (long long)pred;
         if (valid) {
           // confusion index exactly as torch evaluates targets*C + predictions (metrics.py:68)
           const long long idx = (p.label_mode == AWX_LABEL_U8 ? ((t * C) & 0xff) : t * C) + pred;
@@ -188,10 +191,12 @@ __global__ void __launch_bounds__(kThreads, CS > 0 ? 2 : 1) score_kernel(const _
           else
             ++n_bad;
           n_ambig += o[j].ambig;
+          n_eamb += o[j].eamb;
           n_nobin += o[j].bin < 0;
           if (ENS && NB > 0) {
             const bool wrong = t != (long long)o[j].mpred;
             n_wrong += wrong;
+            n_mamb += o[j].mamb;
             float q = floorf(o[j].mi * p.auroc_scale);
             q = is_nan(q) ? 0.f : q;
             const int mb = (int)fminf(fmaxf(q, 0.f), (float)(NB - 1));
@@ -226,9 +231,9 @@ __global__ void __launch_bounds__(kThreads, CS > 0 ? 2 : 1) score_kernel(const _
   if (!have_labels) return;
   // ---- per-thread counters -> CTA
   {
-    unsigned v[8] = {n_valid, n_correct, n_bad, n_ambig, n_wrong, n_pick, n_nobin, n_pix};
+    unsigned v[10] = {n_valid, n_correct, n_bad, n_ambig, n_wrong, n_pick, n_nobin, n_pix, n_mamb, n_eamb};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 10; ++k) {
       const unsigned s = __reduce_add_sync(0xffffffffu, v[k]);
       if (lane == 0 && s) atomicAdd(&s_cnt[k], s);
     }
@@ -256,11 +261,11 @@ __global__ void __launch_bounds__(kThreads, CS > 0 ? 2 : 1) score_kernel(const _
       atomicAdd(bins + p.lay.ece_conf_lo + i, sum_lo);
     }
   }
-  if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(bins + p.lay.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+  if (threadIdx.x < AWX_NUM_COUNTERS && s_cnt[threadIdx.x]) atomicAdd(bins + p.lay.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 size_t score_smem_bytes(int C, int nb, int NB) {
-  return (size_t)kWarps * nb * 16 + ((size_t)C * C + 2 * (size_t)NB + 8) * 4 + (size_t)(nb + 1) * 4;
+  return (size_t)kWarps * nb * 16 + ((size_t)C * C + 2 * (size_t)NB + AWX_NUM_COUNTERS) * 4 + (size_t)(nb + 1) * 4;
 }
 
 template <int CS, int PX, bool ENS, bool JS>
@@ -345,7 +350,7 @@ extern "C" int awx_bins_layout(int32_t C, int32_t nb, int32_t NB, AwxBinsLayout*
   out->ece_conf_lo = o; o += nb;
   out->auroc_pos = o; o += NB;
   out->auroc_neg = o; o += NB;
-  out->counters = o; o += 8;
+  out->counters = o; o += AWX_NUM_COUNTERS;
   out->total_words = o;
   return AWX_OK;
 }
@@ -386,6 +391,7 @@ extern "C" int awx_score(const float* logits_a, const float* logits_b, const voi
   else
     p.div_mode = 2;
   p.rT = (float)(1.0 / (double)cfg->temperature);
+  p.band_abs = p.div_mode == 1 ? 4e-7f * cfg->temperature : 4e-7f;
   p.kz = p.div_mode == 1 ? (float)(1.4426950408889634 / (double)cfg->temperature) : kLog2e;
   p.label_mode = cfg->label_dtype;
   p.ignore_index = cfg->ignore_index;

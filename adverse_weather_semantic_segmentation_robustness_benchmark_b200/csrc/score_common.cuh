@@ -20,7 +20,9 @@ struct ScoreParams {
   float w0, w1, T;
   int div_mode;  // 0: none, 1: T>0 (division only where it can change the argmax), 2: exact everywhere
   float kz;      // log2(e)/T for div_mode 1, log2(e) otherwise
-  float rT;      // fl(1/T), correctly rounded by the host (branch-free exact division, score_v2.cu)
+  float rT;      // fl(1/T), correctly rounded by the host
+  float band_abs;  // absolute half-width of the "top classes may tie" band on the UNdivided fused logits: 4e-7 * T in
+                   // div_mode 1 (a gap of 2.5e-7 between the divided logits is where exp() rounds to 1 - 4 ulp), else 4e-7
   int label_mode;
   int ignore_index;
   int nb;
@@ -41,13 +43,26 @@ struct ScoreParams {
 };
 
 struct PixOut {
-  int pred;
+  int pred;   // arg-max of the fused (divided) logits: confusion matrix, pixel accuracy, the prediction map
+  int epred;  // arg-max of the fused fp32 probabilities: the ECE's accuracy term (metrics.py:161-162)
   float conf;
   int bin;  // -1: in no bin
   int ambig;
   float mi;
-  int mpred;
+  int mpred;  // arg-max of the mean member probabilities (metrics.py:414-416)
   float js;
+  int eamb, mamb;  // the label is one of several classes whose fp32 probabilities may tie for epred / mpred
+};
+
+// relative half-width of the band inside which the approximate mean probabilities of the hot loops (ex2.approx /
+// rcp.approx: ~1e-6 relative) cannot order two classes: such pixels go to resolve_ties
+constexpr float kMargBand = 4e-6f;
+// |vmax| * this + band_abs: two fused logits this close can share a quotient by T, or have fp32 probabilities
+// that tie for the maximum
+constexpr float kPredBandRel = 4.8e-7f;
+
+struct TieOut {
+  int pred, epred, eamb, marg, mamb;
 };
 
 __device__ __forceinline__ float fuse_one(float x, float y, bool mean, float w0, float w1) {
@@ -88,56 +103,147 @@ static __device__ __noinline__ float exact_confidence(const float* ga, const flo
   return cf;
 }
 
+// Rare path (a few pixels per million; every pixel of a region with constant logits): the three arg-maxima of a
+// pixel whose top classes the hot loop could not separate, from global memory.
+//   pred   first index of the maximum of the fused logits exactly as the reference forms them (three roundings,
+//          true division): torch.argmax of the logits (evaluate.py:179, metrics.py:50-51).
+//   epred  the ECE takes torch.max over the fp32 softmax instead (metrics.py:161-162): classes whose divided
+//          logits lie within 2.5e-7 of the maximum have exp(z - zmax) >= 1 - 4 ulp and may come out of torch's
+//          fp32 exp / division EQUAL to the maximum probability, in which case the first of them wins.  Exactly
+//          equal logits tie for certain (first index, no ambiguity).  Otherwise the probabilities are formed in
+//          fp64, rounded to fp32, and the first class equal to the maximum is taken; torch's own result depends
+//          on its vectorised exp, so when the label is one of the candidates the pixel is reported (eamb).
+//   marg   arg-max of (softmax(a) + softmax(b)) / 2 (metrics.py:414-416): candidates are the classes within
+//          8e-7 relative of the fp64 maximum; identical member logits tie for certain; otherwise the fp32 sum of
+//          the fp32-rounded fp64 probabilities decides, reported (mamb) when the label is a candidate.
+static __device__ __noinline__ void resolve_ties(const float* ga, const float* gb, long long HW, int C, bool mean, float w0,
+                                                 float w1, int div_mode, float T, long long lab, bool want_pred,
+                                                 bool want_marg, TieOut& o) {
+  o.pred = o.epred = o.marg = 0;
+  o.eamb = o.mamb = 0;
+  if (want_pred) {
+    float zmax = 0.f;
+    int arg = 0;
+    for (int c = 0; c < C; ++c) {
+      float z = gb ? fuse_one(ga[c * HW], gb[c * HW], mean, w0, w1) : ga[c * HW];
+      if (div_mode) z = __fdiv_rn(z, T);
+      if (c == 0 || beats(z, zmax)) {
+        zmax = z;
+        arg = c;
+      }
+    }
+    o.pred = o.epred = arg;
+    if (!is_nan(zmax)) {
+      double s = 0.0;
+      int ncand = 0, nexact = 0, lab_in = 0;
+      for (int c = 0; c < C; ++c) {
+        float z = gb ? fuse_one(ga[c * HW], gb[c * HW], mean, w0, w1) : ga[c * HW];
+        if (div_mode) z = __fdiv_rn(z, T);
+        const float d = __fsub_rn(z, zmax);
+        s += exp((double)d);
+        if (d >= -2.5e-7f) {
+          ++ncand;
+          nexact += d == 0.f;
+          lab_in |= (long long)c == lab;
+        }
+      }
+      if (ncand > nexact) {
+        const float pmax = (float)(1.0 / s);
+        int first = -1;
+        for (int c = 0; c < C && first < 0; ++c) {
+          float z = gb ? fuse_one(ga[c * HW], gb[c * HW], mean, w0, w1) : ga[c * HW];
+          if (div_mode) z = __fdiv_rn(z, T);
+          const float d = __fsub_rn(z, zmax);
+          if (d >= -2.5e-7f && (float)(exp((double)d) / s) == pmax) first = c;
+        }
+        o.epred = first < 0 ? arg : first;
+        o.eamb = lab_in;
+      }
+    }
+  }
+  if (want_marg && gb) {
+    float amax = ga[0], bmax = gb[0];
+    for (int c = 1; c < C; ++c) {
+      amax = fmaxf(amax, ga[c * HW]);
+      bmax = fmaxf(bmax, gb[c * HW]);
+    }
+    double sa = 0.0, sb = 0.0;
+    for (int c = 0; c < C; ++c) {
+      sa += exp((double)__fsub_rn(ga[c * HW], amax));
+      sb += exp((double)__fsub_rn(gb[c * HW], bmax));
+    }
+    double smax = -1.0;
+    int arg = 0;
+    for (int c = 0; c < C; ++c) {
+      const double m = exp((double)__fsub_rn(ga[c * HW], amax)) / sa + exp((double)__fsub_rn(gb[c * HW], bmax)) / sb;
+      if (m > smax) {
+        smax = m;
+        arg = c;
+      }
+    }
+    o.marg = arg;
+    if (smax == smax && smax > 0.0) {
+      const double thr = smax * (1.0 - 8e-7);
+      int ncand = 0, nsame = 0, lab_in = 0, first = -1;
+      float a0 = 0.f, b0 = 0.f, mbest = -1.f;
+      int best = arg;
+      for (int c = 0; c < C; ++c) {
+        const float av = ga[c * HW], bv = gb[c * HW];
+        const double pa = exp((double)__fsub_rn(av, amax)) / sa, pb = exp((double)__fsub_rn(bv, bmax)) / sb;
+        if (pa + pb >= thr) {
+          if (first < 0) {
+            first = c;
+            a0 = av;
+            b0 = bv;
+          }
+          ++ncand;
+          nsame += (av == a0 && bv == b0);
+          lab_in |= (long long)c == lab;
+          const float m32 = __fadd_rn((float)pa, (float)pb);  // torch: stack(...).mean(0) = fl(p + q) / 2
+          if (m32 > mbest) {
+            mbest = m32;
+            best = c;
+          }
+        }
+      }
+      if (ncand > 1) {
+        o.marg = (nsame == ncand) ? first : best;
+        o.mamb = (nsame == ncand) ? 0 : lab_in;
+      }
+    }
+  }
+}
+
 template <int CS, bool ENS, bool JS>
 __device__ __forceinline__ void score_pixel(float (&a)[CS > 0 ? CS : AWX_MAX_CLASSES],
                                             float (&b)[ENS ? (CS > 0 ? CS : AWX_MAX_CLASSES) : 1], const int C,
                                             const ScoreParams& p, const float* s_edges, const float* ga,
-                                            const float* gb, float w0, float w1, float amax, float bmax, PixOut& o) {
+                                            const float* gb, float w0, float w1, float amax, float bmax, long long lab, PixOut& o) {
   const bool mean = ENS && p.strategy == AWX_FUSE_MEAN;
   const float T = p.T;
-  // ---- pass 1: max / argmax of the fused logits (first index wins ties, NaN wins)
-  float vmax = 0.f;
+  // ---- pass 1: max / argmax of the fused logits (first index wins ties, NaN wins).  The runner-up is tracked
+  // too: when it lies within the band of the maximum, a division by T may merge the two, or their fp32
+  // probabilities may tie (the ECE's arg-max), and resolve_ties settles the pixel from global memory
+  float vmax = 0.f, second = -INFINITY;
   int arg = 0;
-  if (p.div_mode == 1) {
-    float second = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float v = ENS ? fuse_one(a[c], b[ENS ? c : 0], mean, w0, w1) : a[c];
-      if (c == 0) {
-        vmax = v;
-      } else if (beats(v, vmax)) {
-        second = vmax;
-        vmax = v;
-        arg = c;
-      } else {
-        second = fmaxf(second, v);
-      }
-    }
-    // division by T>0 is monotone, but rounding can merge vmax with an earlier, slightly
-    // smaller value; torch's argmax over the divided logits would then return that index.
-    const float tol = fmaxf(fabsf(vmax) * 4.8e-7f, 1e-30f);
-    if (second >= vmax - tol) {
-      const float zmax = __fdiv_rn(vmax, T);
-      for (int c = 0; c < arg; ++c) {
-        const float v = ga ? (gb ? fuse_one(ga[c * p.HW], gb[c * p.HW], mean, w0, w1) : ga[c * p.HW]) : vmax;
-        if (__fdiv_rn(v, T) == zmax) {
-          arg = c;
-          break;
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float v = ENS ? fuse_one(a[c], b[ENS ? c : 0], mean, w0, w1) : a[c];
-      if (p.div_mode == 2) v = __fdiv_rn(v, T);
-      if (c == 0 || beats(v, vmax)) {
-        vmax = v;
-        arg = c;
-      }
+  for (int c = 0; c < C; ++c) {
+    float v = ENS ? fuse_one(a[c], b[ENS ? c : 0], mean, w0, w1) : a[c];
+    if (p.div_mode == 2) v = __fdiv_rn(v, T);
+    if (c == 0) {
+      vmax = v;
+    } else if (beats(v, vmax)) {
+      second = vmax;
+      vmax = v;
+      arg = c;
+    } else {
+      second = fmaxf(second, v);
     }
   }
-  o.pred = arg;
+  o.pred = o.epred = arg;
+  o.eamb = o.mamb = 0;
+  bool tie_pred = C > 1 && second >= vmax - fmaf(fabsf(vmax), kPredBandRel, p.band_abs);
+  bool tie_marg = false;
 
   // ---- pass 2a: softmax denominator of the fused logits -> confidence -> ECE bin
   float sz = 0.f;
@@ -186,18 +292,24 @@ __device__ __forceinline__ void score_pixel(float (&a)[CS > 0 ? CS : AWX_MAX_CLA
     }
     const float ra = __frcp_rn(sa), rb = __frcp_rn(sb);
     const float ka = 0.5f * ra, kb = 0.5f * rb;
-    float hm2 = 0.f, mlm2 = 0.f, mbest = 0.f;
+    float hm2 = 0.f, mlm2 = 0.f, mbest = 0.f, msecond = 0.f;
     int marg = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float m = fmaf(a[c], ka, b[ENS ? c : 0] * kb);
       hm2 = fmaf(m, lg2_approx(m + kEps), hm2);
       if (JS) mlm2 += (m > 0.f) ? m * lg2_approx(m) : 0.f;
-      if (c == 0 || beats(m, mbest)) {
+      if (c == 0) {
+        mbest = m;
+      } else if (beats(m, mbest)) {
+        msecond = mbest;
         mbest = m;
         marg = c;
+      } else {
+        msecond = fmaxf(msecond, m);
       }
     }
+    tie_marg = C > 1 && msecond >= mbest * (1.f - kMargBand);
     const float lsa = kLn2 * lg2_approx(sa), lsb = kLn2 * lg2_approx(sb);
     // H(p) with the reference's eps: -sum p ln(p+eps) ~= ln S - T/S - C*eps (p >> eps)
     const float ceps = (float)C * kEps;
@@ -210,6 +322,19 @@ __device__ __forceinline__ void score_pixel(float (&a)[CS > 0 ? CS : AWX_MAX_CLA
       const float mlp = ka * ta + kb * xba - lsa;
       const float mlq = kb * tb + ka * xab - lsb;
       o.js = kLn2 * mlm2 - 0.5f * (mlp + mlq);
+    }
+  }
+  if ((tie_pred || tie_marg) && ga != nullptr) {
+    TieOut t;
+    resolve_ties(ga, gb, p.HW, C, mean, w0, w1, p.div_mode, T, lab, tie_pred, tie_marg, t);
+    if (tie_pred) {
+      o.pred = t.pred;
+      o.epred = t.epred;
+      o.eamb = t.eamb;
+    }
+    if (tie_marg) {
+      o.mpred = t.marg;
+      o.mamb = t.mamb;
     }
   }
 }

@@ -82,22 +82,30 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// the two floats just below x, for finite |x| > 1e-25 (no zero crossing): step the bit pattern
-// towards smaller values (-1 for positive, +1 for negative numbers)
-__device__ __forceinline__ void float_prev2(float x, float& c1, float& c2) {
-  const int b = __float_as_int(x);
-  const int s = (b >> 31) | 1;
-  c1 = __int_as_float(b - s);
-  c2 = __int_as_float(b - 2 * s);
+// Arg-max of 19 values held as class pairs, with the runner-up test for free.  Bit (18 - c) of the result is
+// set iff x_c < thr: the packed subtraction x - thr handles two classes per instruction and one funnel shift
+// per class collects the sign bits (x == thr gives +0: not below).  With thr a little under the maximum,
+// the complement is the set of classes that may attain it: one bit set -> that class is the arg-max beyond
+// doubt (count-leading-zeros gives its index); several -> resolve_ties (score_common.cuh).  19 + 10 + ~6
+// instructions instead of the 38 of a compare / select chain, which cannot see near ties at all.
+template <int NP>
+__device__ __forceinline__ unsigned below_mask(const float2 (&x)[NP], float thr) {
+  const float2 nt = splat(-thr);
+  unsigned m0 = 0u, m1 = 0u;  // classes 0..9 and 10..18: two independent shift chains
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const float2 d = add2(x[i], nt);
+    if (i < 5) {
+      m0 = __funnelshift_l(__float_as_uint(d.x), m0, 1);
+      m0 = __funnelshift_l(__float_as_uint(d.y), m0, 1);
+    } else {
+      m1 = __funnelshift_l(__float_as_uint(d.x), m1, 1);
+      if (2 * i + 1 < kC) m1 = __funnelshift_l(__float_as_uint(d.y), m1, 1);
+    }
+  }
+  return (m0 << 9) | m1;
 }
-// x / T without branches: q0 = RN(x*y), r = RN(x - q0*T) (exact, FMA), q = RN(q0 + r*y) with
-// y = RN(1/T) from the host is the correctly rounded quotient (Markstein) for normal-range operands;
-// tiny / huge |x| (where the residual could underflow or q overflow) take __fdiv_rn.
-__device__ __forceinline__ float div_by_T(float x, float T, float rT) {
-  const float q0 = x * rT;
-  const float r = fmaf(-q0, T, x);
-  return fmaf(r, rT, q0);
-}
+constexpr unsigned kClassBits = (1u << kC) - 1u;
 
 // (lo, hi] bin of conf; edges are within an ulp of i/nb so the guess is off by at most one
 __device__ __forceinline__ int ece_bin_fast(float conf, const float* e, int nb) {
@@ -109,7 +117,7 @@ __device__ __forceinline__ int ece_bin_fast(float conf, const float* e, int nb) 
 
 // byte offset of the TMA ring inside dynamic shared memory (everything before it is bookkeeping)
 __host__ __device__ inline size_t v2_ring_offset(int cons_warps, int nb, int NB) {
-  size_t o = 2 * kMaxUnits * sizeof(u64) + (8 + 368) * 4 + (AWX_MAX_ECE_BINS + 4) * 4;
+  size_t o = 2 * kMaxUnits * sizeof(u64) + (AWX_NUM_COUNTERS + 368) * 4 + (AWX_MAX_ECE_BINS + 4) * 4;
   o += (size_t)cons_warps * nb * (2 + 2 * kEceRep) * 4 + (size_t)2 * NB * 4;
   return (o + 127) & ~(size_t)127;
 }
@@ -117,7 +125,7 @@ __host__ __device__ inline size_t v2_ring_offset(int cons_warps, int nb, int NB)
 // Slow path for one pixel straight from global memory (NaN / inf logits): the scalar v1 code.
 template <bool ENS, bool JS>
 __device__ __noinline__ void slow_pixel(const ScoreParams& p, const float* s_edges, const float* ga, const float* gb,
-                                        PixOut& o) {
+                                        long long lab, PixOut& o) {
   float a[kC], b[ENS ? kC : 1];
   float amax = 0.f, bmax = 0.f;
   for (int c = 0; c < kC; ++c) {
@@ -145,7 +153,7 @@ __device__ __noinline__ void slow_pixel(const ScoreParams& p, const float* s_edg
     w0 = __frcp_rn(sa) > __frcp_rn(sb) ? 1.f : 0.f;
     w1 = 1.f - w0;
   }
-  score_pixel<kC, ENS, JS>(a, b, kC, p, s_edges, ga, gb, w0, w1, amax, bmax, o);
+  score_pixel<kC, ENS, JS>(a, b, kC, p, s_edges, ga, gb, w0, w1, amax, bmax, lab, o);
 }
 
 // MODE: 0 single member, 1 weighted average, 2 mean, 3 max-confidence (weighted average with per-pixel weights
@@ -190,8 +198,8 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   extern __shared__ __align__(128) unsigned char smem[];
   u64* full = reinterpret_cast<u64*>(smem);              // [kMaxUnits]
   u64* empty = full + kMaxUnits;                         // [kMaxUnits]
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(empty + kMaxUnits);  // [8]
-  unsigned* s_conf = s_cnt + 8;                          // [368] (361 used)
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(empty + kMaxUnits);  // [AWX_NUM_COUNTERS]
+  unsigned* s_conf = s_cnt + AWX_NUM_COUNTERS;                          // [368] (361 used)
   float* s_edges = reinterpret_cast<float*>(s_conf + 368);           // [AWX_MAX_ECE_BINS + 4] (keeps the u64 arrays 8-byte aligned)
   // per-warp ECE words.  Counts take the value 1 (the hardware aggregates lanes hitting the same word:
   // ATOMS.POPC.INC, ~3 wavefronts); the confidence sums carry per-lane values, and a shared-memory atomic add
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   float* units = reinterpret_cast<float*>(smem + v2_ring_offset(kConsWarps, nb, NB));
   {
     unsigned* w = s_cnt;
-    const int words = 8 + 368;
+    const int words = AWX_NUM_COUNTERS + 368;
     for (int i = threadIdx.x; i < words; i += kV2Threads) w[i] = 0u;
     unsigned* w2 = w_cnt;
     const int words2 = kConsWarps * nb * (2 + 2 * kEceRep) + 2 * NB;
@@ -357,6 +365,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     float mi = 0.f, js = 0.f, sa = 1.f, sb = 1.f;
     float amax = a[0].x, bmax = b[0].x;
     int marg = 0;
+    bool tie_u = false;  // several classes may attain the maximum of the mean probabilities
     auto members_phase = [&]() {
     if (ENS) {
       float2 sa2 = splat(0.f), sb2 = splat(0.f), ta2 = splat(0.f), tb2 = splat(0.f), xab2 = splat(0.f), xba2 = splat(0.f);
@@ -403,10 +412,11 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         a[i] = uu;  // keep the (unnormalised) mean probabilities for the arg-max below
         umax = fmaxf(umax, fmaxf(uu.x, uu.y));
       }
-#pragma unroll
-      for (int i = NP - 1; i >= 0; --i) {
-        if (2 * i + 1 < kC) marg = (a[i].y == umax) ? 2 * i + 1 : marg;
-        marg = (a[i].x == umax) ? 2 * i : marg;
+      if (NB > 0) {
+        // arg-max of the mean probabilities (the AUROC's positive flag): classes within kMargBand of the maximum
+        const unsigned cand = ~below_mask<NP>(a, umax * (1.f - kMargBand)) & kClassBits;
+        marg = __clz(cand) - (32 - kC);
+        tie_u = __popc(cand) != 1;
       }
       // entropies in bits: H2(p) = lg2 S' - (sum e'_c t_c)/S'; the reference's log(p + eps) adds
       // -C*eps nats (p >> eps)
@@ -496,25 +506,13 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         bmax = fmaxf(bmax, fmaxf(b[ENS ? i : 0].x, b[ENS ? i : 0].y));
       }
     }
-    // first index attaining the max.  With a division by T > 0 still pending (div_mode 1) the
-    // quotient can merge the max with the one or two floats just below it (at most 3 inputs share
-    // a quotient); torch's argmax over the divided logits returns the first of those, so compare
-    // against the smallest float whose quotient equals the max quotient.
-    float vlo = vmax;
-    if (div_mode == 1) {
-      // branch-free exact quotients; |vmax| outside [1e-25, 1e25] is routed to the scalar slow
-      // path below (residual underflow / quotient overflow), so this block stays straight-line
-      float c1, c2;
-      float_prev2(vmax, c1, c2);
-      const float zmax = div_by_T(vmax, T, p.rT), z1 = div_by_T(c1, T, p.rT), z2 = div_by_T(c2, T, p.rT);
-      vlo = (z1 == zmax) ? ((z2 == zmax) ? c2 : c1) : vmax;
-    }
-    int arg = 0;
-#pragma unroll
-    for (int i = NP - 1; i >= 0; --i) {
-      if (2 * i + 1 < kC) arg = (v[i].y >= vlo) ? 2 * i + 1 : arg;
-      arg = (v[i].x >= vlo) ? 2 * i : arg;
-    }
+    // Arg-max of the fused logits.  Classes within the band of the maximum are candidates: a pending division by
+    // T > 0 (div_mode 1) can merge the maximum only with values a few ulp below it (torch's argmax over the divided
+    // logits then returns the first of them), and the ECE's arg-max over fp32 probabilities can tie only within
+    // 2.5e-7 of the divided maximum; a single candidate is the arg-max of both, anything else is resolved exactly.
+    const unsigned cand_v = ~below_mask<NP>(v, vmax - fmaf(fabsf(vmax), kPredBandRel, p.band_abs)) & kClassBits;
+    const int arg = __clz(cand_v) - (32 - kC);
+    const bool tie_v = __popc(cand_v) != 1;
 
     // optional fused-logit output (bit exact: div_mode is 0 or 2 whenever it is requested)
     if (FAST == 0 && p.fused != nullptr && act) {
@@ -544,13 +542,12 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     if (MODE != 3) members_phase();
 
     // ---- confidence, ECE bin, slow paths
-    int pred = arg, bin, ambig = 0;
+    int pred = arg, epred = arg, bin, ambig = 0;
     float conf;
     {
-      const bool range_ok = div_mode != 1 || (fabsf(vmax) > 1e-25f && fabsf(vmax) < 1e25f);
       // one finiteness test: every term is >= 1 or tiny, so the sum is non-finite iff a term is
       const float chk = ENS ? (sz + sa) + (sb + mi) : sz;
-      const bool sane = range_ok && fabsf(chk) < 3e38f;
+      const bool sane = fabsf(chk) < 3e38f;
       const float r0 = rcp_approx(sz);
       const float r = fmaf(r0, fmaf(-sz, r0, 1.f), r0);  // one Newton step: <= 1 ulp
       conf = fminf(fmaf(r, zdelta, r), 1.f);
@@ -576,31 +573,54 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
           near = (bin > 0 && (conf - s_edges[bin]) <= tol) || (bin < nb - 1 && (s_edges[bin + 1] - conf) <= tol);
         }
       }
-      if (act && (!sane || near)) {
+      const bool tie = tie_v || (ENS && tie_u);
+      if (act && (!sane || near || tie)) {
         const long long go = (long long)img * kC * HW + p0 + t;
         const float* ga = p.a + go;
         const float* gb = ENS ? p.b + go : nullptr;
+        int eamb = 0, mamb = 0;
         if (!sane) {
           PixOut so;
-          slow_pixel<ENS, JS>(p, s_edges, ga, gb, so);
+          slow_pixel<ENS, JS>(p, s_edges, ga, gb, lab, so);
           pred = so.pred;
+          epred = so.epred;
           conf = so.conf;
           bin = so.bin;
           ambig = so.ambig;
           mi = so.mi;
           js = so.js;
           marg = so.mpred;
+          eamb = so.eamb;
+          mamb = so.mamb;
         } else {
-          int amb = 0;
-          conf = exact_confidence(ga, gb, HW, kC, MODE == 2, w0s, w1s, div_mode, T, s_edges, nb, &amb);
-          ambig = amb;
-          bin = ece_bin(conf, s_edges, nb);
+          if (near) {
+            int amb = 0;
+            conf = exact_confidence(ga, gb, HW, kC, MODE == 2, w0s, w1s, div_mode, T, s_edges, nb, &amb);
+            ambig = amb;
+            bin = ece_bin(conf, s_edges, nb);
+          }
+          if (tie) {
+            TieOut to;
+            resolve_ties(ga, gb, HW, kC, MODE == 2, w0s, w1s, div_mode, T, lab, tie_v, ENS && tie_u, to);
+            if (tie_v) {
+              pred = to.pred;
+              epred = to.epred;
+              eamb = to.eamb;
+            }
+            if (ENS && tie_u) {
+              marg = to.marg;
+              mamb = to.mamb;
+            }
+          }
         }
-        // bookkeeping that only these rare pixels can need: the ambiguity count, and correct pixels that
-        // fall in no ECE bin (every other correct pixel is counted through its bin's packed word)
+        // bookkeeping that only these rare pixels can need: the ambiguity counts, and AWX_CNT_CORRECT (arg-max of
+        // the LOGITS == label), which every other pixel contributes through its ECE bin's packed `correct` word
+        // (arg-max of the PROBABILITIES == label): add the difference, or the whole term for a pixel in no bin
         if (have_labels && lab != ignore) {
           n_ambig += ambig;
-          if (bin < 0 && lab == pred) ++n_correct;
+          if (eamb) atomicAdd(&s_cnt[AWX_CNT_EPRED_AMBIG], 1u);
+          if (mamb && NB > 0) atomicAdd(&s_cnt[AWX_CNT_MARG_AMBIG], 1u);
+          n_correct += (unsigned)((int)(lab == pred) - (bin >= 0 ? (int)(lab == epred) : 0));
         }
       }
     }
@@ -637,7 +657,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       }
       since_flush += 32u;
       const bool valid = act && lab != ignore;
-      const bool correct = valid && lab == pred;
+      const bool correct = valid && lab == epred;  // the ECE's accuracy term (arg-max of the probabilities)
       int ckey = -1, akey = -1;
       if (valid) {
         // confusion index as torch evaluates targets*C + predictions (uint8 product wraps mod 256)
@@ -769,6 +789,8 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     if (s_cnt[AWX_CNT_ECE_AMBIG]) atomicAdd(bins + p.lay.counters + AWX_CNT_ECE_AMBIG, (u64)s_cnt[AWX_CNT_ECE_AMBIG]);
     if (s_cnt[AWX_CNT_ENS_WRONG]) atomicAdd(bins + p.lay.counters + AWX_CNT_ENS_WRONG, (u64)s_cnt[AWX_CNT_ENS_WRONG]);
     if (s_cnt[AWX_CNT_PICK_AMBIG]) atomicAdd(bins + p.lay.counters + AWX_CNT_PICK_AMBIG, (u64)s_cnt[AWX_CNT_PICK_AMBIG]);
+    if (s_cnt[AWX_CNT_MARG_AMBIG]) atomicAdd(bins + p.lay.counters + AWX_CNT_MARG_AMBIG, (u64)s_cnt[AWX_CNT_MARG_AMBIG]);
+    if (s_cnt[AWX_CNT_EPRED_AMBIG]) atomicAdd(bins + p.lay.counters + AWX_CNT_EPRED_AMBIG, (u64)s_cnt[AWX_CNT_EPRED_AMBIG]);
     if (nobin) atomicAdd(bins + p.lay.counters + AWX_CNT_NO_BIN, (u64)nobin);
     if (blockIdx.x == 0) atomicAdd(bins + p.lay.counters + AWX_CNT_PIXELS, (u64)(p.B * p.HW));
   }

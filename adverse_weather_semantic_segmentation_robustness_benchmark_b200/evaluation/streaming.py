@@ -107,7 +107,10 @@ class StreamingEvaluator:
             "pixel_accuracy": b.counter(_lib.CNT_CORRECT) / valid if valid else 0.0,
             "expected_calibration_error": finalize.ece_from_bins(
                 b.ece_count, b.ece_correct, b.ece_conf_sum, valid, ops.ece_edges(self.ece_bins).numpy())["ece"],
+            # pixels whose integer outcome lies inside the reference's own fp32 rounding noise (include/awx.h)
             "ece_ambiguous_pixels": b.counter(_lib.CNT_ECE_AMBIG),
+            "epred_ambiguous_pixels": b.counter(_lib.CNT_EPRED_AMBIG),
+            "marg_ambiguous_pixels": b.counter(_lib.CNT_MARG_AMBIG),
             "pixels": b.counter(_lib.CNT_PIXELS),
         }
         if self.auroc_bins:

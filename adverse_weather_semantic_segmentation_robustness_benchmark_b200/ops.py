@@ -218,7 +218,7 @@ def members_n(members, labels: Optional[torch.Tensor] = None, *, ignore_index: i
               auroc_hi: Optional[float] = None, want_mi: bool = False, want_var: bool = False) -> dict:
     """awx_members_n: disagreement of a list of N >= 2 members ([B,C,H,W] fp32 each).  Returns a dict with the
     requested maps (``mi`` [B,H,W], ``var`` [B,C,H,W]) and, with labels, ``pos`` / ``neg`` (int64 [auroc_bins]) and
-    ``counters`` (int64 [8]).  The MI of N members lies in [0, ln N): that is the default histogram range."""
+    ``counters`` (int64 [NUM_COUNTERS]).  The MI of N members lies in [0, ln N): that is the default histogram range."""
     lib = _lib.load()
     ms = [to_device(m, torch.float32) for m in members]
     if len(ms) < 2:
@@ -240,7 +240,7 @@ def members_n(members, labels: Optional[torch.Tensor] = None, *, ignore_index: i
     if lab is not None:
         out["pos"] = torch.zeros(max(auroc_bins, 1), dtype=torch.int64, device=dev)
         out["neg"] = torch.zeros(max(auroc_bins, 1), dtype=torch.int64, device=dev)
-        out["counters"] = torch.zeros(8, dtype=torch.int64, device=dev)
+        out["counters"] = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
     ptrs = (C.c_void_p * len(ms))(*[m.data_ptr() for m in ms])
     hi = float(auroc_hi) if auroc_hi is not None else math.log(len(ms))
     rc = lib.awx_members_n(ptrs, len(ms), _ptr(lab), _lib.LABEL_I64 if lab is None else label_code(lab), bsz, ncls, h * w,
@@ -289,7 +289,7 @@ def fuse_backward(grad_fused: torch.Tensor, logits_a: torch.Tensor, logits_b: to
 
 
 def confusion(pred: torch.Tensor, labels: torch.Tensor, num_classes: int, ignore_index: int = 255):
-    """(confusion int64 [C,C] device tensor, counters int64 [8] device tensor) from prediction maps."""
+    """(confusion int64 [C,C] device tensor, counters int64 [NUM_COUNTERS] device tensor) from prediction maps."""
     lib = _lib.load()
     lab = normalise_labels(labels).reshape(-1)
     if pred.dtype not in (torch.uint8, torch.int64):
@@ -299,7 +299,7 @@ def confusion(pred: torch.Tensor, labels: torch.Tensor, num_classes: int, ignore
         raise ValueError(f"predictions ({prd.numel()}) and targets ({lab.numel()}) differ in size")
     dev = require_cuda()
     cm = torch.zeros(num_classes * num_classes, dtype=torch.int64, device=dev)
-    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(_lib.NUM_COUNTERS, dtype=torch.int64, device=dev)
     rc = lib.awx_confusion(_ptr(prd), _lib.PRED_U8 if prd.dtype == torch.uint8 else _lib.PRED_I64,
                            _ptr(lab), label_code(lab), prd.numel(), num_classes, ignore_index,
                            _ptr(cm), _ptr(cnt), _stream())

@@ -470,13 +470,30 @@ def parity_object(wl, results, world):
     """Parity gates reported with the benchmark: the step's own counters, a small probe of the
     hot path against the CPU oracle (N = 1 only: the oracle is the checker here, never the thing measured), and
     the versions of the libraries whose arithmetic the oracle calls."""
-    out = {"ece_ambiguous_pixels": int(sum(v.get("ece_ambiguous_pixels", 0) for v in wl.ev.per_condition().values())),
-           "overall_miou": results.get("overall_miou")}
+    per = wl.ev.per_condition()
+    out = {"overall_miou": results.get("overall_miou"), "step_pixels": int(sum(v["pixels"] for v in per.values()))}
+    for key in ("ece_ambiguous_pixels", "epred_ambiguous_pixels", "marg_ambiguous_pixels"):
+        out[key] = int(sum(v.get(key, 0) for v in per.values()))
     if world == 1:
+        import torch
+        import __graft_entry__ as entry
         try:
-            import __graft_entry__ as entry
-            out["oracle_probe"] = entry.parity_probe()
+            # ONE FULL FRAME of the step's own inputs through the kernel the step launches (bins only), against the
+            # oracle on the host: true mismatch of every integer output next to the reported ambiguous pixels
+            ev = wl.ev
+            got = wl.ops.read_bins(wl.ops.score(wl.la[:1], wl.lb[:1], wl.labels[:1], strategy=ev.strategy, w0=ev.w0, w1=ev.w1,
+                                                temperature=ev.temperature, auroc_bins=ev.auroc_bins)["bins"],
+                                   NUM_CLASSES, 15, ev.auroc_bins)
+            full = entry.bins_vs_oracle(got, wl.la[:1].cpu(), wl.lb[:1].cpu(), wl.labels[:1].cpu(),
+                                        torch.tensor(RAW_WEIGHTS), TEMPERATURE, NUM_CLASSES)
+            out["full_frame"] = full
+            out["ece_true_mismatch"] = full["ece_true_mismatch"]
+            out["ens_wrong_mismatch"] = full["ens_wrong_mismatch"]
         except Exception as exc:  # a failed gate must be visible in the line, not kill the measurement
+            out["full_frame"] = {"failed": repr(exc)[:300]}
+        try:
+            out["oracle_probe"] = entry.parity_probe()
+        except Exception as exc:
             out["oracle_probe"] = {"failed": repr(exc)[:300]}
     try:
         import cv2, numpy, scipy, sklearn, torch

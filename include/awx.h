@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AWX_VERSION 100 /* major*100 + minor */
+#define AWX_VERSION 101 /* major*100 + minor */
 
 #define AWX_OK 0
 #define AWX_E_ARG (-1)         /* null / negative / inconsistent argument       */
@@ -38,6 +38,7 @@ extern "C" {
 #define AWX_MAX_CLASSES 64
 #define AWX_MAX_ECE_BINS 64
 #define AWX_MAX_AUROC_BINS 8192
+#define AWX_NUM_COUNTERS 16 /* words of the `counters` block of a bins buffer (AWX_CNT_*) */
 
 int awx_version(void);
 const char* awx_last_error(void);
@@ -106,7 +107,7 @@ typedef struct AwxScoreMaps {
  *   ece_conf_hi[nb], ece_conf_lo[nb]   sum of conf in 2^-31 fixed point = hi*2^32 + lo; both words are plain
  *                          accumulators (lo may exceed 2^32), so equal sums need not be equal word by word
  *   auroc_pos  [NB], auroc_neg[NB]     MI histogram of wrong / right ensemble pixels
- *   counters   [8]        AWX_CNT_*                                                   */
+ *   counters   [AWX_NUM_COUNTERS]  AWX_CNT_*                                          */
 typedef struct AwxBinsLayout {
   int64_t confusion, ece_count, ece_correct, ece_conf_hi, ece_conf_lo;
   int64_t auroc_pos, auroc_neg, counters, total_words;
@@ -114,14 +115,21 @@ typedef struct AwxBinsLayout {
 
 enum {
   AWX_CNT_VALID = 0,     /* label != ignore_index                                          */
-  AWX_CNT_CORRECT = 1,   /* valid and argmax(fused) == label                               */
+  AWX_CNT_CORRECT = 1,   /* valid and argmax(fused LOGITS) == label (pixel accuracy, :110-123) */
   AWX_CNT_BAD_LABEL = 2, /* valid but confusion index outside [0,C*C): reference raises    */
   AWX_CNT_ECE_AMBIG = 3, /* valid pixels whose confidence is within 3 fp32 ulp of an
                             interior bin edge (the reference's own rounding noise)          */
   AWX_CNT_ENS_WRONG = 4, /* valid and argmax(mean member prob) != label (AUROC positives)  */
   AWX_CNT_PICK_AMBIG = 5,/* MAXCONF: member confidences within 4 ulp of each other         */
   AWX_CNT_NO_BIN = 6,    /* valid pixels whose confidence fell in no bin (0, NaN)          */
-  AWX_CNT_PIXELS = 7     /* all pixels seen                                                */
+  AWX_CNT_PIXELS = 7,    /* all pixels seen                                                */
+  /* The reference takes two of its arg-maxima over fp32 PROBABILITIES (torch softmax, not reproducible bit for
+   * bit across builds / thread counts).  A pixel whose top classes are closer than that arithmetic's rounding
+   * noise is re-evaluated in fp64 (resolve_ties, csrc/score_common.cuh); when the label is one of the tied
+   * classes -- the only case in which an integer output can depend on the outcome -- it is counted here, so
+   * |bins - reference bins| is bounded by these counters and nothing else. */
+  AWX_CNT_MARG_AMBIG = 8,  /* arg-max of the mean member probabilities (AUROC positives, :414-416)  */
+  AWX_CNT_EPRED_AMBIG = 9  /* arg-max of the fused probabilities (ECE accuracy term, :161-162)      */
 };
 
 int awx_bins_layout(int32_t num_classes, int32_t ece_bins, int32_t auroc_bins, AwxBinsLayout* out /*HOST*/);
@@ -137,7 +145,7 @@ int awx_score(const float* logits_a, const float* logits_b, const void* labels,
  * [B,H,W] predictions, evaluation/metrics.py:53-71, 110-123).  pred: AWX_PRED_* dtype, labels:
  * AWX_LABEL_* dtype, n elements each.  The index is formed with torch's type promotion:
  * uint8*C wraps mod 256, and uint8 labels + uint8 predictions wrap as a whole.
- * confusion: int64 [C*C]; counters: int64 [8] (AWX_CNT_VALID / _CORRECT / _BAD_LABEL / _PIXELS). */
+ * confusion: int64 [C*C]; counters: int64 [AWX_NUM_COUNTERS] (AWX_CNT_VALID / _CORRECT / _BAD_LABEL / _PIXELS). */
 int awx_confusion(const void* pred, int32_t pred_dtype, const void* labels, int32_t label_dtype, int64_t n,
                   int32_t num_classes, int32_t ignore_index, int64_t* confusion, int64_t* counters, void* stream);
 
@@ -149,7 +157,8 @@ int awx_member_variance(const float* logits_a, const float* logits_b, float* out
 /* EnsembleDisagreementMetrics for a LIST of N >= 2 members (evaluation/metrics.py:336-438; two members run inside
  * awx_score): mi_out [B,HW] = H(mean_k p_k) - mean_k H(p_k); var_out [B,C,HW] = unbiased variance over members;
  * with labels: auroc_pos / auroc_neg int64 [auroc_bins] histograms of mi over [0, auroc_hi) for pixels whose
- * argmax(mean p) != / == label, counters int64 [8] (AWX_CNT_VALID, AWX_CNT_ENS_WRONG, AWX_CNT_PIXELS); all accumulate.
+ * argmax(mean p) != / == label, counters int64 [AWX_NUM_COUNTERS] (AWX_CNT_VALID, AWX_CNT_ENS_WRONG, AWX_CNT_MARG_AMBIG,
+ * AWX_CNT_PIXELS); all accumulate.
  * members: HOST array of n_members device pointers to fp32 [B,C,HW]; every output pointer may be NULL. */
 int awx_members_n(const float* const* members /*HOST*/, int32_t n_members, const void* labels, int32_t label_dtype,
                   int64_t batch, int32_t num_classes, int64_t pixels_per_image, int32_t ignore_index,

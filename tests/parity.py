@@ -1,0 +1,55 @@
+"""Integer-parity gates shared by the GPU tests (and mirrored by bench.py's `parity` object).
+
+The reference derives three integer quantities from fp32 PROBABILITIES (torch's softmax), which no other
+implementation can reproduce bit for bit: the ECE bin of a pixel, the arg-max of the fused probabilities (the
+ECE's accuracy term) and the arg-max of the mean member probabilities (the AUROC's positive flag).  The CUDA
+path re-evaluates every pixel that is close to such a decision boundary in fp64 and COUNTS those for which the
+outcome is inside the reference's own rounding noise (AWX_CNT_ECE_AMBIG / _EPRED_AMBIG / _MARG_AMBIG).  The
+gates below make those counters the only slack:
+
+* the counters themselves are bounded (a kernel that flags half the frame cannot pass);
+* the TRUE mismatch against the oracle -- pixels sitting in a different ECE bin, `correct` flags that differ,
+  ensemble-wrong flags that differ -- must not exceed the corresponding counter.
+"""
+
+import numpy as np
+
+
+def amb_bound(n_valid: int, per_pixel: float = 2e-6, floor: int = 0) -> int:
+    """Upper bound on a self-reported ambiguity counter: `per_pixel` of the valid pixels (+ `floor` for the
+    small frames of the unit tests, where one unlucky pixel is already more than 2e-6 of the frame)."""
+    return int(np.floor(per_pixel * n_valid)) + floor
+
+
+def ece_mismatch(bins, ref: dict) -> dict:
+    """True mismatch of the ECE bins against the oracle's integer counts."""
+    d_count = np.abs(np.asarray(bins.ece_count) - ref["count"])
+    d_correct = np.abs(np.asarray(bins.ece_correct) - ref["correct"])
+    # a pixel binned differently shows up in two bins; an odd total means the in-no-bin count differs too
+    return {"moved_pixels": int((d_count.sum() + 1) // 2), "correct_l1": int(d_correct.sum())}
+
+
+def assert_ece_parity(bins, ref: dict, n_valid: int, _lib, per_pixel: float = 2e-6, floor: int = 0,
+                      extra_amb: int = 0) -> dict:
+    """ECE counts == the oracle's up to the pixels the kernel itself reports as ambiguous, those being few."""
+    amb = bins.counter(_lib.CNT_ECE_AMBIG) + extra_amb
+    eamb = bins.counter(_lib.CNT_EPRED_AMBIG)
+    cap = amb_bound(n_valid, per_pixel, floor)
+    assert amb <= cap + extra_amb, f"{amb} ECE-ambiguous pixels reported, more than {cap} ({per_pixel:g} of {n_valid})"
+    assert eamb <= cap, f"{eamb} prediction-ambiguous pixels reported, more than {cap}"
+    mm = ece_mismatch(bins, ref)
+    assert mm["moved_pixels"] <= amb, f"{mm['moved_pixels']} pixels binned differently, only {amb} reported ambiguous"
+    # a moved pixel that is correct changes two `correct` bins; a prediction-ambiguous pixel changes one
+    assert mm["correct_l1"] <= 2 * amb + eamb, (mm, amb, eamb)
+    mm.update(ece_ambiguous=amb, epred_ambiguous=eamb)
+    return mm
+
+
+def assert_ens_wrong_parity(bins, wrong_ref: int, n_valid: int, _lib, per_pixel: float = 2e-6, floor: int = 0) -> dict:
+    """AWX_CNT_ENS_WRONG (= sum of the AUROC positives) == the oracle's count up to AWX_CNT_MARG_AMBIG."""
+    mamb = bins.counter(_lib.CNT_MARG_AMBIG)
+    cap = amb_bound(n_valid, per_pixel, floor)
+    assert mamb <= cap, f"{mamb} mean-probability ties reported, more than {cap}"
+    diff = abs(bins.counter(_lib.CNT_ENS_WRONG) - int(wrong_ref))
+    assert diff <= mamb, f"ensemble-wrong count differs by {diff}, only {mamb} pixels reported ambiguous"
+    return {"ens_wrong_mismatch": diff, "marg_ambiguous": mamb}

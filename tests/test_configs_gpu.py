@@ -12,6 +12,7 @@ import pytest
 import torch
 
 from oracle import weather as ow, metrics as om, fusion as of_, loss as ol
+import parity
 
 pytestmark = pytest.mark.gpu
 C = 19
@@ -56,8 +57,9 @@ def test_config0_fog_and_confusion_on_20_synthetic_frames(pkg):
 
 
 def test_config2_ensemble_fusion_full_frame(pkg):
-    """One 19x1024x2048 frame per member: fused logits bit-exact, arg-max / confusion ==, ECE bins == up to the
-    reported ambiguous pixels, MI map and AUROC within the stated tolerances."""
+    """One 19x1024x2048 frame per member: fused logits bit-exact, arg-max / confusion ==; ECE bins and the
+    ensemble-wrong count == the oracle's up to the pixels the kernel reports as ambiguous, which must be fewer than
+    2e-6 of the frame (tests/parity.py); MI map and AUROC within the stated tolerances."""
     p, ops, _lib = pkg
     gen = torch.Generator().manual_seed(42)
     la = torch.randn(1, C, 1024, 2048, generator=gen)
@@ -76,9 +78,12 @@ def test_config2_ensemble_fusion_full_frame(pkg):
     bins = ops.read_bins(out["bins"], C, 15, 4096)
     assert np.array_equal(bins.confusion, om.confusion_matrix(want, tgt, C).numpy())
     ref = om.ece(want, tgt)
-    amb = bins.counter(_lib.CNT_ECE_AMBIG)
-    assert np.abs(bins.ece_count - ref["count"]).sum() <= 2 * amb
-    assert np.abs(bins.ece_correct - ref["correct"]).sum() <= 2 * amb
+    valid = tgt != 255
+    n_valid = int(valid.sum())
+    parity.assert_ece_parity(bins, ref, n_valid, _lib)
+    assert bins.counter(_lib.CNT_CORRECT) == int(((want.argmax(1) == tgt) & valid).sum())
+    wrong = int(((om.mean_prob_prediction([la, lb]) != tgt) & valid).sum())
+    parity.assert_ens_wrong_parity(bins, wrong, n_valid, _lib)
     conf_ref, _ = om.confidence_and_prediction(want)
     assert (out["conf"].cpu() - conf_ref).abs().max() <= 2.4e-7
     mi_ref = om.mi_map([la, lb])
@@ -90,7 +95,9 @@ def test_config2_ensemble_fusion_full_frame(pkg):
     fast = ops.read_bins(ops.score(la, lb, tgt, strategy=_lib.FUSE_WEIGHTED, w0=float(w[0]), w1=float(w[1]),
                                    temperature=1.7, auroc_bins=4096)["bins"], C, 15, 4096)
     assert np.array_equal(fast.confusion, bins.confusion)
-    assert np.abs(fast.ece_count - ref["count"]).sum() <= 2 * (amb + fast.counter(_lib.CNT_ECE_AMBIG))
+    parity.assert_ece_parity(fast, ref, n_valid, _lib)
+    parity.assert_ens_wrong_parity(fast, wrong, n_valid, _lib)
+    assert fast.counter(_lib.CNT_CORRECT) == bins.counter(_lib.CNT_CORRECT)
 
 
 def test_config3_loss_forward_backward_batch8(pkg):

@@ -27,14 +27,14 @@ def test_library_exports_every_declared_symbol(lib):
     assert declared == set(lib.exported_symbols()), declared ^ set(lib.exported_symbols())
     for name in declared:
         assert getattr(handle, name) is not None
-    assert handle.awx_version() == 100
+    assert handle.awx_version() == 101
     assert handle.awx_launch_count() == 0
 
 
 def test_bins_layout_and_argument_errors(lib):
     lay = lib.bins_layout(19, 15, 4096)
     assert lay.confusion == 0 and lay.ece_count == 361
-    assert lay.total_words == 361 + 4 * 15 + 2 * 4096 + 8
+    assert lay.total_words == 361 + 4 * 15 + 2 * 4096 + lib.NUM_COUNTERS
     with pytest.raises(RuntimeError, match="num_classes"):
         lib.bins_layout(65, 15, 0)
     with pytest.raises(RuntimeError, match="ece_bins"):

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import metrics as om, fusion as of_
+import parity
 
 pytestmark = pytest.mark.gpu
 C = 19
@@ -54,9 +55,7 @@ def test_score_fuzz(seed):
         assert np.array_equal(bins.confusion, om.confusion_matrix(want, tgt, C).numpy())
         assert bins.counter(_lib.CNT_CORRECT) == int(((want.argmax(1) == tgt) & valid).sum())
         ref = om.ece(want, tgt)
-        amb = bins.counter(_lib.CNT_ECE_AMBIG)
-        assert np.abs(bins.ece_count - ref["count"]).sum() <= 2 * amb
-        assert np.abs(bins.ece_correct - ref["correct"]).sum() <= 2 * amb
+        parity.assert_ece_parity(bins, ref, int(valid.sum()), _lib, floor=2)
         conf_ref, _ = om.confidence_and_prediction(want)
         # 3 ulp at 1.0, plus the reference's own rounding of z = v/T before its softmax (~ulp(|z|max) relative):
         # the kernel keeps the exact quotient in the exponent, so it is the more accurate of the two
@@ -67,7 +66,7 @@ def test_score_fuzz(seed):
     err = (out["mi"].cpu() - mi_ref).abs() - (1e-5 * mi_ref.abs() + 2e-6)
     assert float(err.max()) <= 0, f"MI excess {float(err.max()):.2e}"
     wrong = (om.mean_prob_prediction([la, lb]) != tgt) & valid
-    assert abs(bins.counter(_lib.CNT_ENS_WRONG) - int(wrong.sum())) <= 2   # exact ties of the mean probabilities aside
+    parity.assert_ens_wrong_parity(bins, int(wrong.sum()), int(valid.sum()), _lib, floor=2)
     # bins only
     fast = ops.read_bins(ops.score(la, lb, tgt, **kw)["bins"], C, 15, 4096)
     assert np.array_equal(fast.confusion, bins.confusion)

@@ -39,11 +39,11 @@ def short(n):
     return re.sub(r"\(.*", "", n)
 
 
-out = ["# ptxas resource usage of every kernel in libawx.so (sm_100a, final build of round 1)", "",
+out = ["# ptxas resource usage of every kernel in libawx.so (sm_100a, round 2)", "",
        "`nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Xptxas -v` (`tools/ptxas_resources.py`); static shared memory only "
        "(the score / blur / temperature kernels add dynamic shared memory at launch).", "",
        "| kernel | registers | stack B | spill stores B | static smem B |", "|---|---|---|---|---|"]
 for n, (k, r) in sorted(zip(map(short, names), rows.items())):
     out.append(f"| `{n}` | {r['regs']} | {r['stack']} | {r['spill']} | {r['smem']} |")
-open(os.path.join(b.ROOT, "profiles", "r1_ptxas_resources.md"), "w").write("\n".join(out) + "\n")
+open(os.path.join(b.ROOT, "profiles", os.environ.get("AWX_PTXAS_OUT", "r2_ptxas_resources.md")), "w").write("\n".join(out) + "\n")
 print(len(rows), "kernels")
