@@ -47,7 +47,7 @@ def _digest() -> str:
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     files += sorted(os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())   # repo-relative: the stamp is valid in any checkout dir
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

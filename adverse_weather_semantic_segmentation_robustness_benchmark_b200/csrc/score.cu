@@ -348,9 +348,11 @@ extern "C" int awx_bins_layout(int32_t C, int32_t nb, int32_t NB, AwxBinsLayout*
   out->ece_correct = o; o += nb;
   out->ece_conf_hi = o; o += nb;
   out->ece_conf_lo = o; o += nb;
+  out->counters = o; o += AWX_NUM_COUNTERS;
+  // the AUROC histograms come last: a buffer laid out for NB > 0 is a valid target for launches without them
+  // (single-member scoring), which makes one buffer size fit every rank of a sharded evaluation
   out->auroc_pos = o; o += NB;
   out->auroc_neg = o; o += NB;
-  out->counters = o; o += AWX_NUM_COUNTERS;
   out->total_words = o;
   return AWX_OK;
 }

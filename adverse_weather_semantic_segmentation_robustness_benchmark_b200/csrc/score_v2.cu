@@ -21,6 +21,10 @@
 #include "score_common.cuh"
 #include "tma_ring.cuh"
 
+#ifndef AWX_V2_GROUPS
+#define AWX_V2_GROUPS 3
+#endif
+
 namespace awx {
 using namespace score_detail;
 namespace {
@@ -37,7 +41,24 @@ struct Geo {
   static constexpr int kThreads = kCons + 32;    // + producer warp
   static constexpr int kUnitFloats = kC * kTP;
   static constexpr int kUnitBytes = kUnitFloats * 4;
+  // Consumer warps form kGroups GROUPS, each waiting for its own CHUNK (pixel range) of a ring unit on its own pair
+  // of barriers.  The producer issues the chunks of a tile one after the other, so they land a third of a tile's
+  // transfer time apart and the groups run out of phase: while one pulls its pixels out of shared memory (LDS),
+  // another is in its exponentials (MUFU) and the third in the packed arithmetic.  With ONE barrier per unit all
+  // warps started every tile together and queued for the same pipe (measured: forcing lock-step with a named
+  // barrier costs 12 %; mio_throttle is the top stall either way).
+  static constexpr int kGroups = (AWX_V2_GROUPS <= CW) ? AWX_V2_GROUPS : 1;
+  __host__ __device__ static constexpr int group_first_warp(int g) {   // groups differ by at most one warp
+    return g * (CW / kGroups) + (g < CW % kGroups ? g : CW % kGroups);
+  }
+  __host__ __device__ static constexpr int group_warps(int g) { return CW / kGroups + (g < CW % kGroups ? 1 : 0); }
+  __host__ __device__ static constexpr int group_of_warp(int w) {
+    int g = 0;
+    for (int i = 1; i < kGroups; ++i) g += (w >= group_first_warp(i)) ? 1 : 0;
+    return g;
+  }
 };
+constexpr int kMaxGroups = 5;
 constexpr int kMaxUnits = 4;                    // ring depth for one member (2 units of both members for an ensemble):
                                                 // 1.5, 2 and 2.5 tiles measure the same; the shared memory is better
                                                 // spent on conflict-free statistics
@@ -117,7 +138,7 @@ __device__ __forceinline__ int ece_bin_fast(float conf, const float* e, int nb) 
 
 // byte offset of the TMA ring inside dynamic shared memory (everything before it is bookkeeping)
 __host__ __device__ inline size_t v2_ring_offset(int cons_warps, int nb, int NB) {
-  size_t o = 2 * kMaxUnits * sizeof(u64) + (AWX_NUM_COUNTERS + 368) * 4 + (AWX_MAX_ECE_BINS + 4) * 4;
+  size_t o = 2 * kMaxUnits * kMaxGroups * sizeof(u64) + (AWX_NUM_COUNTERS + 368) * 4 + (AWX_MAX_ECE_BINS + 4) * 4;
   o += (size_t)cons_warps * nb * (2 + 2 * kEceRep) * 4 + (size_t)2 * NB * 4;
   return (o + 127) & ~(size_t)127;
 }
@@ -196,9 +217,9 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   const int NB = FAST != 0 ? (ENS ? kFastAurocBins : 0) : p.auroc_bins;
   const bool have_labels = FAST != 0 || p.labels != nullptr;
   extern __shared__ __align__(128) unsigned char smem[];
-  u64* full = reinterpret_cast<u64*>(smem);              // [kMaxUnits]
-  u64* empty = full + kMaxUnits;                         // [kMaxUnits]
-  unsigned* s_cnt = reinterpret_cast<unsigned*>(empty + kMaxUnits);  // [AWX_NUM_COUNTERS]
+  u64* full = reinterpret_cast<u64*>(smem);              // [kMaxUnits][kMaxGroups]
+  u64* empty = full + kMaxUnits * kMaxGroups;            // [kMaxUnits][kMaxGroups]
+  unsigned* s_cnt = reinterpret_cast<unsigned*>(empty + kMaxUnits * kMaxGroups);  // [AWX_NUM_COUNTERS]
   unsigned* s_conf = s_cnt + AWX_NUM_COUNTERS;                          // [368] (361 used)
   float* s_edges = reinterpret_cast<float*>(s_conf + 368);           // [AWX_MAX_ECE_BINS + 4] (keeps the u64 arrays 8-byte aligned)
   // per-warp ECE words.  Counts take the value 1 (the hardware aggregates lanes hitting the same word:
@@ -221,8 +242,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     for (int i = threadIdx.x; i <= nb; i += kV2Threads) s_edges[i] = p.edges[i];
     if (threadIdx.x == 0) {
       for (int u = 0; u < NU; ++u) {
-        mbar_init(full + u, 1);
-        mbar_init(empty + u, kConsWarps);
+        for (int g = 0; g < G::kGroups; ++g) {
+          mbar_init(full + u * kMaxGroups + g, 1);
+          mbar_init(empty + u * kMaxGroups + g, G::group_warps(g));
+        }
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -243,23 +266,33 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     long long img = blockIdx.x / tpi, tin = blockIdx.x - img * tpi;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long p0 = tin * kTP;
-      const unsigned npx = (unsigned)((HW - p0) < kTP ? (HW - p0) : kTP);
-      mbar_wait(empty + u, ph ^ 1u);
-      // ONE thread issues the 19 (38) copies of the unit from warp-uniform operands: the copy instruction takes
-      // uniform registers, and per-lane addresses would make the compiler broadcast every lane's operands one
-      // after the other (ELECT / 4 x R2UR / UBLKCP per copy: ~190 instructions per unit, which kept this warp
-      // busy 70 % of the time)
-      if (elect_one()) {
-        mbar_expect_tx(full + u, (ENS ? 2u : 1u) * kC * npx * 4u);
-        float* dst = units + (size_t)u * kUnitFloats;
+      const int npx = (int)((HW - p0) < kTP ? (HW - p0) : kTP);
 #pragma unroll
-        for (int m = 0; m < (ENS ? 2 : 1); ++m) {
-          const float* src = (m == 0 ? p.a : p.b) + img * kC * HW + p0;
+      for (int g = 0; g < G::kGroups; ++g) {
+        // chunk g of the unit: the pixels of consumer group g (nothing for a group past the end of the image, whose
+        // barrier still completes: expect_tx of 0 bytes is a plain arrival)
+        const int c0 = 32 * G::group_first_warp(g), cn = 32 * G::group_warps(g);
+        const int n = min(max(npx - c0, 0), cn);
+        u64* fb = full + u * kMaxGroups + g;
+        mbar_wait(empty + u * kMaxGroups + g, ph ^ 1u);
+        // ONE thread issues the 19 (38) copies of the chunk from warp-uniform operands: the copy instruction takes
+        // uniform registers, and per-lane addresses would make the compiler broadcast every lane's operands one
+        // after the other (ELECT / 4 x R2UR / UBLKCP per copy: ~190 instructions per unit, which kept this warp
+        // busy 70 % of the time)
+        if (elect_one()) {
+          mbar_expect_tx(fb, (ENS ? 2u : 1u) * kC * (unsigned)n * 4u);
+          if (n > 0) {
+            float* dst = units + (size_t)u * kUnitFloats + c0;
 #pragma unroll
-          for (int c = 0; c < kC; ++c) bulk_load(dst + (m * kC + c) * kTP, src + c * HW, npx * 4u, full + u);
+            for (int m = 0; m < (ENS ? 2 : 1); ++m) {
+              const float* src = (m == 0 ? p.a : p.b) + img * kC * HW + p0 + c0;
+#pragma unroll
+              for (int c = 0; c < kC; ++c) bulk_load(dst + (m * kC + c) * kTP, src + c * HW, (unsigned)n * 4u, fb);
+            }
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
       if (++u == (unsigned)NU) {
         u = 0;
         ph ^= 1u;
@@ -288,7 +321,9 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   const uint32_t conf_sa = smem_u32(s_conf), auroc_sa = smem_u32(s_auroc);
   const uint32_t cnt_sa = smem_u32(w_cnt + warp * nb), cor_sa = smem_u32(w_cor + warp * nb);
   const uint32_t lo_sa = smem_u32(my_lo) + 4u * (lane & (kEceRep - 1)), hi_sa = smem_u32(my_hi) + 4u * (lane & (kEceRep - 1));
-  const uint32_t sbase = smem_u32(smem);                                  // full[u] at sbase + 8u, empty[u] at + 8(kMaxUnits + u)
+  // this warp's group: full[u][grp] at my_bar0 + 8 kMaxGroups u, empty[u][grp] kMaxUnits * kMaxGroups words further
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t my_bar0 = sbase + 8u * (uint32_t)G::group_of_warp(warp);
   const uint32_t my_unit0 = sbase + (uint32_t)v2_ring_offset(kConsWarps, nb, NB) + 4u * (uint32_t)t;
   // B * HW < 2^32 (score_v2_supported): all pixel and tile indices of the consumers are 32 bit
   const unsigned HWu = (unsigned)HW, tpiu = (unsigned)tpi, ntu = (unsigned)ntiles;
@@ -314,7 +349,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
     float2 a[NP], b[ENS ? NP : 1];
     uint32_t held_unit, held_bar;
     {
-      mbar_wait_a(sbase + 8u * u, ph);
+      mbar_wait_a(my_bar0 + 8u * kMaxGroups * u, ph);
       const uint32_t s = my_unit0 + u * kUnitBytes;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
@@ -330,7 +365,7 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       }
       // max-confidence kernels keep the unit until the winning member's logits have been re-read (see P0)
       held_unit = s;
-      held_bar = sbase + 8u * (kMaxUnits + u);
+      held_bar = my_bar0 + 8u * kMaxGroups * (kMaxUnits + u);
       if (MODE != 3) {
         __syncwarp();
         if (lane == 0) mbar_arrive_a(held_bar);
@@ -423,7 +458,10 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       // only lg2 Sa' + lg2 Sb' = lg2(Sa' Sb') enters the mutual information: one logarithm
       const float lsab = lg2_approx(sab);
       const float ceps = (float)kC * kEps;
-      mi = kLn2 * (-kas * (hm2.x + hm2.y) - 0.5f * (lsab - tsa * ra - tsb * rb)) + ceps;
+      // explicit roundings: every instantiation of this kernel (bins-only / generic, all strategies) must produce the
+      // same MI bit pattern for a pixel, or the AUROC histograms of two code paths differ at bin edges
+      const float hsum = __fmaf_rn(-tsb, rb, __fmaf_rn(-tsa, ra, lsab));
+      mi = __fmaf_rn(kLn2, __fmaf_rn(-0.5f, hsum, __fmul_rn(-kas, __fadd_rn(hm2.x, hm2.y))), ceps);
       if (JS) {
         // sum_c m_c lg2 p_c = ka*Ta + kb*Xba - lg2 Sa' ; sum_c m_c lg2 q_c = kb*Tb + ka*Xab - lg2 Sb'
         const float xab = xab2.x + xab2.y, xba = xba2.x + xba2.y;

@@ -52,6 +52,26 @@ __device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity) {
         : "memory");
   } while (!ok);
 }
+// one bounded attempt: true once the phase with the given parity has completed (sleeps up to `ns` otherwise)
+__device__ __forceinline__ bool mbar_try(u64* bar, unsigned parity, unsigned ns) {
+  unsigned ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking test
+__device__ __forceinline__ bool mbar_test(u64* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsigned bytes, u64* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst_smem)),

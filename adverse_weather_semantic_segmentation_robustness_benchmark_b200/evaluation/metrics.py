@@ -95,16 +95,29 @@ class ConfidenceCalibration:
             "bin_proportions": np.array([d["proportion"] for d in keep]),
         }
 
-    def temperature_scale(self, logits: torch.Tensor, temperature: float) -> torch.Tensor:
-        """metrics.py:266-281: logits / temperature (true fp32 division), materialised by awx_score."""
+    def temperature_scale(self, logits: torch.Tensor, temperature) -> torch.Tensor:
+        """metrics.py:266-281: ``logits / temperature`` (true fp32 division).  Like the reference's eager division
+        it is differentiable w.r.t. the logits and a tensor temperature: with grad mode on and either requiring
+        grad, the quotient goes through the fusion autograd function as the mean of the logits with themselves,
+        (x + x) / 2 / T = x / T bit for bit, whose backward kernel returns g / T and the sum for dL/dT."""
+        wants_grad = torch.is_grad_enabled() and (
+            (torch.is_tensor(logits) and logits.requires_grad)
+            or (torch.is_tensor(temperature) and temperature.requires_grad))
+        if wants_grad:
+            from ..models.model import _FuseFn
+            x = ops.to_device(logits, torch.float32)
+            t = temperature if torch.is_tensor(temperature) else torch.tensor([float(temperature)])
+            flat = x if x.dim() == 4 else x.reshape(1, 1, -1, 1)
+            return _FuseFn.apply(flat, flat, None, t.reshape(-1)[:1], "mean").reshape(x.shape)
+        temperature = float(temperature.detach().reshape(-1)[0]) if torch.is_tensor(temperature) else float(temperature)
         x = _as_logits(logits)
         squeeze = x.dim() != 4
         if squeeze:
             # [N, C] or other layouts: present as [1, C, N, 1] with classes on dim 1 is not the same
             # memory order; elementwise division does not care about the layout, so flatten.
             flat = x.reshape(1, 1, -1, 1)
-            return ops.score(flat, temperature=float(temperature), want_fused=True)["fused"].reshape(x.shape)
-        return ops.score(x, temperature=float(temperature), want_fused=True)["fused"]
+            return ops.score(flat, temperature=temperature, want_fused=True)["fused"].reshape(x.shape)
+        return ops.score(x, temperature=temperature, want_fused=True)["fused"]
 
     def optimize_temperature(self, logits: torch.Tensor, targets: torch.Tensor, max_iter: int = 50) -> float:
         """metrics.py:283-321: 100-point grid search of the NLL over T in linspace(0.1, 10)."""

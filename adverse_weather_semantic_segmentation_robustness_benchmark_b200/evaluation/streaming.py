@@ -33,7 +33,10 @@ class StreamingEvaluator:
         self.conditions = tuple(conditions)
         self.ece_bins = ece_bins
         self.ensemble = ensemble
-        self.auroc_bins = auroc_bins if ensemble else 0
+        # the buffer is always laid out WITH the AUROC histograms (they come last, include/awx.h): single-member
+        # launches touch only the prefix, so every rank of a sharded evaluation holds the same number of words
+        # whatever its shard contains, and one all_reduce fits all
+        self.auroc_bins = auroc_bins
         self.ignore_index = ignore_index
         self.temperature = temperature
         codes = {"weighted_average": _lib.FUSE_WEIGHTED, "max_confidence": _lib.FUSE_MAXCONF}
@@ -47,6 +50,7 @@ class StreamingEvaluator:
         # always needs the CUDA device)
         dev = ops.require_cuda() if bins_device is None else torch.device(bins_device)
         self.bins = torch.zeros((len(self.conditions), self.words), dtype=torch.int64, device=dev)
+        self._scratch = None
         self._cfg_cache = {}
 
     def reset(self) -> None:
@@ -56,9 +60,32 @@ class StreamingEvaluator:
                labels: torch.Tensor) -> None:
         """Score one batch of one condition: a single awx_score launch, nothing is materialised."""
         row = self.bins[self.conditions.index(condition)]
-        ops.score(logits_a, logits_b if self.ensemble else None, labels, strategy=self.strategy,
-                  w0=self.w0, w1=self.w1, temperature=self.temperature, ignore_index=self.ignore_index,
-                  ece_bins=self.ece_bins, auroc_bins=self.auroc_bins, bins=row)
+        ens = self.ensemble and logits_b is not None
+        ops.score(logits_a, logits_b if ens else None, labels, strategy=self.strategy if ens else _lib.FUSE_SINGLE,
+                  w0=self.w0, w1=self.w1, temperature=self.temperature if ens else None,
+                  ignore_index=self.ignore_index, ece_bins=self.ece_bins, auroc_bins=self.auroc_bins if ens else 0,
+                  bins=row)
+
+    def update_members(self, condition: str, fused: torch.Tensor, logits_a: torch.Tensor, logits_b: torch.Tensor,
+                       labels: torch.Tensor) -> None:
+        """The general form of evaluate.py:178-201 for a model whose fusion this package cannot restate: the
+        confusion matrix and the ECE bins come from the model's OWN ``outputs['segmentation']`` (one single-member
+        launch), the disagreement histogram from the two members (a second launch into a scratch buffer, of which
+        only the AUROC words and their counters are kept)."""
+        idx = self.conditions.index(condition)
+        row = self.bins[idx]
+        ops.score(fused, None, labels, strategy=_lib.FUSE_SINGLE, temperature=None, ignore_index=self.ignore_index,
+                  ece_bins=self.ece_bins, auroc_bins=0, bins=row)
+        if self._scratch is None:
+            self._scratch = torch.zeros(self.words, dtype=torch.int64, device=self.bins.device)
+        self._scratch.zero_()
+        ops.score(logits_a, logits_b, labels, strategy=_lib.FUSE_MEAN, temperature=None, ignore_index=self.ignore_index,
+                  ece_bins=self.ece_bins, auroc_bins=self.auroc_bins, bins=self._scratch)
+        lay = self.layout
+        hist = slice(int(lay.auroc_pos), int(lay.auroc_pos) + 2 * self.auroc_bins)   # pos and neg are adjacent
+        row[hist] += self._scratch[hist]
+        for k in (_lib.CNT_ENS_WRONG, _lib.CNT_MARG_AMBIG):
+            row[int(lay.counters) + k] += self._scratch[int(lay.counters) + k]
 
     def update_corrupted(self, condition: str, images: torch.Tensor, params, field, items, out: torch.Tensor,
                          workspace: torch.Tensor, logits_a: torch.Tensor, logits_b: Optional[torch.Tensor],
@@ -113,7 +140,7 @@ class StreamingEvaluator:
             "marg_ambiguous_pixels": b.counter(_lib.CNT_MARG_AMBIG),
             "pixels": b.counter(_lib.CNT_PIXELS),
         }
-        if self.auroc_bins:
+        if self.auroc_bins and (self.ensemble or int(b.auroc_pos.sum() + b.auroc_neg.sum()) > 0):
             out["ensemble_disagreement_auroc"], out["auroc_bound"] = finalize.auroc_from_histogram(
                 b.auroc_pos, b.auroc_neg)
         return out
@@ -137,7 +164,7 @@ class StreamingEvaluator:
             res[f"miou_{c}"] = m["mean_iou"]
             res[f"ece_{c}"] = m["expected_calibration_error"]
         res["expected_calibration_error"] = total["expected_calibration_error"]
-        if self.auroc_bins:
+        if "ensemble_disagreement_auroc" in total:
             res["ensemble_disagreement_auroc"] = total["ensemble_disagreement_auroc"]
         if "clean" in mious:
             degr = []
@@ -153,44 +180,89 @@ class StreamingEvaluator:
 OTHER = "__other__"
 
 
+def _unwrap(model):
+    """The module inside DistributedDataParallel / DataParallel style wrappers (``.module``)."""
+    seen = 0
+    while isinstance(getattr(model, "module", None), torch.nn.Module) and seen < 4:
+        model = model.module
+        seen += 1
+    return model
+
+
+def _fusion_of(core):
+    """(strategy, raw ensemble weights, temperature | None) of an EnsembleModel-like module, or None when it does
+    not carry the reference's fusion attributes (models/model.py:385-426) -- nothing is ever defaulted."""
+    if not all(hasattr(core, a) for a in ("ensemble_strategy", "ensemble_weights", "temperature_scaling")):
+        return None
+    ts = bool(core.temperature_scaling)
+    if ts and not hasattr(core, "temperature"):
+        return None
+    raw_w = core.ensemble_weights.detach().float().cpu().reshape(-1)
+    if raw_w.numel() != 2:
+        return None
+    temp = float(core.temperature.detach().float().cpu().reshape(-1)[0]) if ts else None
+    return str(core.ensemble_strategy), raw_w.tolist(), temp
+
+
 def evaluate_model(model, test_loader, metrics=None, device=None, config=None, group=None) -> Dict[str, float]:
     """Drop-in for the reference's ``evaluate_model(model, test_loader, metrics, device, config)``
     (scripts/evaluate.py:134-274; trainer twin training/trainer.py:377-478), streaming and sharded.
 
     Same loop -- ``outputs = model(images)`` per batch, frames grouped by ``batch['weather_condition']`` --
-    but nothing is concatenated: every run of consecutive frames with the same condition is scored by one
-    ``awx_score`` launch into that condition's integer bins.  An ensemble model (outputs carry
-    ``segformer_seg`` and ``deeplabv3plus_seg``) is fused inside the kernel with the model's own
-    ``ensemble_strategy`` / ``ensemble_weights`` / ``temperature``; any other model is scored on
-    ``outputs['segmentation']``.  Under ``torch.distributed`` every rank evaluates its shard of the loader
-    and one ``all_reduce`` merges the bins.  ``metrics`` / ``device`` are accepted for signature
-    compatibility (``metrics.num_classes`` and ``metrics.weather_conditions`` are honoured)."""
+    but nothing is concatenated: every run of consecutive frames with the same condition is scored on the device
+    into that condition's integer bins.  What is scored is what the reference scores: ``outputs['segmentation']``
+    for mIoU / ECE and, for an ensemble (``hasattr(model, 'segformer')`` and member logits in the outputs,
+    evaluate.py:196), the two members for the disagreement AUROC.  When the (unwrapped) model carries the
+    reference's fusion attributes AND re-fusing the first batch's members in the kernel reproduces its
+    ``outputs['segmentation']`` bit for bit, the fusion is done inside the scoring kernel (one launch, 152 B/px
+    instead of 229); otherwise the model's own fused logits are scored and the members only feed the histogram.
+    Under ``torch.distributed`` every rank evaluates its shard of the loader -- an empty shard included -- and one
+    ``all_reduce`` merges the bins.  ``metrics.num_classes`` / ``metrics.weather_conditions`` are honoured."""
+    from ..models.model import _STRATEGY, _fuse_forward
     get = (lambda k, d: config.get(k, d)) if config is not None and hasattr(config, "get") else (lambda k, d: d)
     conditions = list(get("data.weather_conditions", None) or getattr(metrics, "weather_conditions", None)
                       or DEFAULT_CONDITIONS)
     num_classes = int(getattr(metrics, "num_classes", None) or get("model.num_classes", 19))
-    ev = None
+    core = _unwrap(model)
+    fusion = _fusion_of(core)
+    dev = torch.device(device) if device is not None else ops.require_cuda()
+    if dev.type != "cuda":
+        raise RuntimeError("evaluate_model scores on a CUDA device (libawx.so has no CPU path); got device=%s" % dev)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    strategy, raw_w, temp = fusion if fusion is not None else ("mean", [0.5, 0.5], None)
+    # built BEFORE the loop: a rank whose shard is empty still owns (zero) bins of the common size for the all_reduce
+    ev = StreamingEvaluator(num_classes, conditions + [OTHER], strategy=strategy, ensemble_weights=raw_w,
+                            temperature=temp, ensemble=True, bins_device=dev)
+    ev.ensemble_seen = False
+    in_kernel = None     # decided on the first ensemble batch
     was_training = getattr(model, "training", False)
     if hasattr(model, "eval"):
         model.eval()
     with torch.no_grad():
         for batch in test_loader:
-            images = batch["image"].to(device) if device is not None else batch["image"]
-            labels = batch["label"].to(device) if device is not None else batch["label"]
+            images = batch["image"].to(dev)
+            labels = batch["label"].to(dev)
             weather = list(batch.get("weather_condition", ["clean"] * images.size(0)))
             outputs = model(images)
-            ensemble = "segformer_seg" in outputs and "deeplabv3plus_seg" in outputs
-            if ev is None:
-                if ensemble:
-                    ts = bool(getattr(model, "temperature_scaling", False))
-                    raw_w = getattr(model, "ensemble_weights", torch.ones(2) / 2).detach().float().cpu()
-                    temp = float(model.temperature.detach().float().cpu()[0]) if ts else None
-                    ev = StreamingEvaluator(num_classes, conditions + [OTHER], strategy=getattr(model, "ensemble_strategy", "mean"),
-                                            ensemble_weights=raw_w.tolist(), temperature=temp, ensemble=True)
-                else:
-                    ev = StreamingEvaluator(num_classes, conditions + [OTHER], ensemble=False, temperature=None)
-            la = outputs["segformer_seg"] if ensemble else outputs["segmentation"]
-            lb = outputs["deeplabv3plus_seg"] if ensemble else None
+            seg = outputs.get("segmentation")
+            # evaluate.py:196: ensemble statistics only for a model that HAS a `segformer` member
+            members = hasattr(model, "segformer") and "segformer_seg" in outputs and "deeplabv3plus_seg" in outputs
+            la = lb = None
+            if members:
+                la, lb = outputs["segformer_seg"].to(dev), outputs["deeplabv3plus_seg"].to(dev)
+                ev.ensemble_seen = True
+                if in_kernel is None:
+                    in_kernel = False
+                    if fusion is not None:
+                        w = torch.softmax(torch.tensor(raw_w, dtype=torch.float32), dim=0)
+                        code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
+                        in_kernel = seg is None or bool(torch.equal(
+                            _fuse_forward(la, lb, code, float(w[0]), float(w[1]), temp), seg.to(dev).float()))
+            if seg is None and not (members and in_kernel):
+                raise KeyError("model outputs carry no 'segmentation' logits and the model has no fusion attributes "
+                               "(ensemble_strategy / ensemble_weights / temperature) to rebuild them from")
+            seg = None if seg is None else seg.to(dev)
             # runs of consecutive frames with the same condition are contiguous views: no copies
             i = 0
             while i < len(weather):
@@ -198,12 +270,19 @@ def evaluate_model(model, test_loader, metrics=None, device=None, config=None, g
                 while j + 1 < len(weather) and weather[j + 1] == weather[i]:
                     j += 1
                 cond = weather[i] if weather[i] in conditions else OTHER
-                ev.update(cond, la[i:j + 1], None if lb is None else lb[i:j + 1], labels[i:j + 1])
+                sl = slice(i, j + 1)
+                if members and in_kernel:
+                    ev.update(cond, la[sl], lb[sl], labels[sl])
+                elif members:
+                    ev.update_members(cond, seg[sl], la[sl], lb[sl], labels[sl])
+                else:
+                    ev.update(cond, seg[sl], None, labels[sl])
                 i = j + 1
     if was_training and hasattr(model, "train"):
         model.train()
-    if ev is None:
-        return {}
     ev.all_reduce(group)
+    ev.ensemble = False    # the AUROC key appears iff some rank scored member logits (its histogram is non-empty)
+    host = ev.bins.cpu()
+    if not bool(host.any()):
+        return {}          # nothing evaluated anywhere (the reference's torch.cat of an empty list raises here)
     return ev.finalize()
-

@@ -65,12 +65,13 @@ def validate_epoch(model, val_loader, loss_fn, metrics=None, device=None, group=
 
     num_classes = int(getattr(metrics, "num_classes", None) or 19)
     conditions = list(weather_conditions)
-    ev = StreamingEvaluator(num_classes, conditions + [OTHER], ensemble=False, temperature=None)
+    dev = ops.require_cuda() if device is None else torch.device(device)
+    ev = StreamingEvaluator(num_classes, conditions + [OTHER], auroc_bins=0, ensemble=False, temperature=None,
+                            bins_device=dev)
     fog_aware = isinstance(loss_fn, FogDensityAwareLoss)
     was_training = getattr(model, "training", False)
     if hasattr(model, "eval"):
         model.eval()
-    dev = ops.require_cuda() if device is None else torch.device(device)
     terms, sizes = [], []       # per batch: [total, seg, depth] device scalars (read back once) and the batch size
     with torch.no_grad():
         for batch in val_loader:

@@ -65,10 +65,23 @@ class EnsembleModel(nn.Module):
         temp = float(self.temperature.detach().float().cpu()[0]) if self.temperature_scaling else None
         return float(w[0]), float(w[1]), temp
 
+    def _wants_graph(self, a: torch.Tensor, b: torch.Tensor, with_weights: bool, with_temperature: bool) -> bool:
+        """The reference's eager expression always carries autograd to the members, ``ensemble_weights`` and
+        ``temperature`` (models/model.py:443-462), in train() and eval() mode alike: take the differentiable path
+        whenever grad mode is on and ANY of them requires grad (frozen backbones with a trainable temperature --
+        post-hoc calibration in eval mode -- included)."""
+        if not torch.is_grad_enabled():
+            return False
+        params = []
+        if with_weights:
+            params.append(self.ensemble_weights)
+        if with_temperature and self.temperature_scaling:
+            params.append(self.temperature)
+        return a.requires_grad or b.requires_grad or any(p.requires_grad for p in params)
+
     def fuse(self, seg1: torch.Tensor, seg2: torch.Tensor) -> torch.Tensor:
         """Fused, temperature-scaled logits (model.py:443-462), bit-exact w.r.t. torch eager."""
-        if torch.is_grad_enabled() and (seg1.requires_grad or seg2.requires_grad
-                                        or self.ensemble_weights.requires_grad and self.training):
+        if self._wants_graph(seg1, seg2, self.ensemble_strategy == "weighted_average", True):
             return _FuseFn.apply(seg1, seg2, self.ensemble_weights,
                                  self.temperature if self.temperature_scaling else None,
                                  self.ensemble_strategy)
@@ -79,8 +92,7 @@ class EnsembleModel(nn.Module):
     def fuse_depth(self, d1: torch.Tensor, d2: torch.Tensor) -> torch.Tensor:
         """model.py:471-478: weighted for weighted_average, plain mean otherwise; no temperature."""
         strategy = "weighted_average" if self.ensemble_strategy == "weighted_average" else "mean"
-        if torch.is_grad_enabled() and (d1.requires_grad or d2.requires_grad
-                                        or self.ensemble_weights.requires_grad and self.training):
+        if self._wants_graph(d1, d2, strategy == "weighted_average", False):
             return _FuseFn.apply(d1, d2, self.ensemble_weights, None, strategy)
         w0, w1, _ = self._fusion_scalars()
         code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
@@ -126,8 +138,10 @@ class _FuseFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b, raw_w, temperature, strategy):
-        w = F.softmax(raw_w.detach().float().cpu(), dim=0)
-        w0, w1 = float(w[0]), float(w[1])
+        w0 = w1 = 0.5
+        if raw_w is not None:
+            w = F.softmax(raw_w.detach().float().cpu(), dim=0)
+            w0, w1 = float(w[0]), float(w[1])
         temp = None if temperature is None else float(temperature.detach().float().reshape(-1)[0])
         code = _STRATEGY.get(strategy, _lib.FUSE_MEAN)
         fused = _fuse_forward(a, b, code, w0, w1, temp)
@@ -141,7 +155,7 @@ class _FuseFn(torch.autograd.Function):
         w0, w1, temp, code, raw_w, temperature = ctx.meta
         ga, gb, dots = ops.fuse_backward(g, a, b, code, w0, w1, temp, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         gw = gt = None
-        need_w = ctx.needs_input_grad[2] and code == _lib.FUSE_WEIGHTED
+        need_w = raw_w is not None and ctx.needs_input_grad[2] and code == _lib.FUSE_WEIGHTED
         need_t = temperature is not None and ctx.needs_input_grad[3]
         if need_w or need_t:
             d = dots.cpu()   # three fp64 scalars

@@ -7,6 +7,7 @@ passes raw ``data_ptr()``s to libawx.so.  Nothing falls back to torch arithmetic
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 from dataclasses import dataclass
 from typing import Optional
@@ -26,6 +27,36 @@ def require_cuda() -> torch.device:
             "adverse_weather_semantic_segmentation_robustness_benchmark_b200 needs a CUDA device: "
             "its arithmetic lives in libawx.so (sm_100a) and there is no CPU fallback.")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def _tensors_in(args, kwargs):
+    for v in list(args) + list(kwargs.values()):
+        if torch.is_tensor(v):
+            yield v
+        elif isinstance(v, (list, tuple)):
+            for u in v:
+                if torch.is_tensor(u):
+                    yield u
+
+
+def device_scoped(fn):
+    """Run `fn` with the device of its CUDA operands current.  The library sizes its grids from cudaGetDevice(),
+    the wrappers allocate outputs / workspaces on the current device and hand over ITS current stream, and host
+    operands are uploaded to it -- so a call on tensors of cuda:1 while cuda:0 is current must switch first
+    (otherwise kernels on device 0 would dereference device-1 pointers).  Operands on two different CUDA devices
+    raise instead of silently going through peer access."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if not torch.cuda.is_available():
+            return fn(*args, **kwargs)          # fn raises the "needs a CUDA device" error itself
+        devs = {t.device for t in _tensors_in(args, kwargs) if t.is_cuda}
+        if len(devs) > 1:
+            raise ValueError(f"{fn.__name__}: operands live on different CUDA devices: {sorted(map(str, devs))}")
+        if not devs or next(iter(devs)).index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(next(iter(devs))):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def to_device(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -115,9 +146,9 @@ class Bins:
         return int(self.raw[self.layout.counters + which])
 
 
-def new_bins(num_classes: int, ece_bins: int = 15, auroc_bins: int = 0) -> torch.Tensor:
+def new_bins(num_classes: int, ece_bins: int = 15, auroc_bins: int = 0, device=None) -> torch.Tensor:
     lay = _lib.bins_layout(num_classes, ece_bins, auroc_bins)
-    return torch.zeros(lay.total_words, dtype=torch.int64, device=require_cuda())
+    return torch.zeros(lay.total_words, dtype=torch.int64, device=require_cuda() if device is None else device)
 
 
 def score_config(num_classes: int, strategy: int, w0: float, w1: float, temperature: Optional[float], label_dtype: int,
@@ -136,6 +167,7 @@ def score_config(num_classes: int, strategy: int, w0: float, w1: float, temperat
     return cfg
 
 
+@device_scoped
 def score(logits_a: torch.Tensor, logits_b: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None, *,
           strategy: int = _lib.FUSE_SINGLE, w0: float = 0.5, w1: float = 0.5,
           temperature: Optional[float] = None, ignore_index: int = 255,
@@ -202,6 +234,7 @@ def read_bins(bins: torch.Tensor, num_classes: int, ece_bins: int = 15, auroc_bi
     return Bins(bins.cpu().numpy(), num_classes, ece_bins, auroc_bins)
 
 
+@device_scoped
 def member_variance(logits_a: torch.Tensor, logits_b: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     a = to_device(logits_a, torch.float32)
@@ -214,6 +247,7 @@ def member_variance(logits_a: torch.Tensor, logits_b: torch.Tensor) -> torch.Ten
     return out
 
 
+@device_scoped
 def members_n(members, labels: Optional[torch.Tensor] = None, *, ignore_index: int = 255, auroc_bins: int = 0,
               auroc_hi: Optional[float] = None, want_mi: bool = False, want_var: bool = False) -> dict:
     """awx_members_n: disagreement of a list of N >= 2 members ([B,C,H,W] fp32 each).  Returns a dict with the
@@ -250,6 +284,7 @@ def members_n(members, labels: Optional[torch.Tensor] = None, *, ignore_index: i
     return out
 
 
+@device_scoped
 def fuse_forward(logits_a: torch.Tensor, logits_b: torch.Tensor, strategy: int, w0: float, w1: float,
                  temperature: Optional[float]) -> torch.Tensor:
     """awx_fuse_forward: the fused logits of two [B,C,H,W] members (EnsembleModel.forward), nothing else."""
@@ -267,6 +302,7 @@ def fuse_forward(logits_a: torch.Tensor, logits_b: torch.Tensor, strategy: int, 
     return out
 
 
+@device_scoped
 def fuse_backward(grad_fused: torch.Tensor, logits_a: torch.Tensor, logits_b: torch.Tensor, strategy: int, w0: float,
                   w1: float, temperature: Optional[float], want_a: bool = True, want_b: bool = True):
     """awx_fuse_backward: (grad_a | None, grad_b | None, dots fp64[3] device) for the fusion's backward pass."""
@@ -288,6 +324,7 @@ def fuse_backward(grad_fused: torch.Tensor, logits_a: torch.Tensor, logits_b: to
     return ga, gb, dots
 
 
+@device_scoped
 def confusion(pred: torch.Tensor, labels: torch.Tensor, num_classes: int, ignore_index: int = 255):
     """(confusion int64 [C,C] device tensor, counters int64 [NUM_COUNTERS] device tensor) from prediction maps."""
     lib = _lib.load()
@@ -312,6 +349,7 @@ def corrupt_workspace(batch: int, height: int, width: int) -> torch.Tensor:
     return torch.empty(max(int(n), 16), dtype=torch.uint8, device=require_cuda())
 
 
+@device_scoped
 def corrupt(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tensor] = None,
             items: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
             workspace: Optional[torch.Tensor] = None, norm_out: Optional[torch.Tensor] = None,
@@ -370,6 +408,7 @@ def corrupt(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tens
     return out if write_u8 else norm_out
 
 
+@device_scoped
 def corrupt_score(images: torch.Tensor, params: np.ndarray, field: Optional[torch.Tensor], items: Optional[torch.Tensor],
                   out: torch.Tensor, workspace: torch.Tensor, logits_a: torch.Tensor, logits_b: Optional[torch.Tensor],
                   labels: torch.Tensor, cfg, bins: torch.Tensor) -> None:

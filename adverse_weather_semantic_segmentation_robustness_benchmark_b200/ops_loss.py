@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .ops import _ptr, _stream
+from .ops import _ptr, _stream, device_scoped
 
 
 def _loss_workspace() -> torch.Tensor:
@@ -17,6 +17,7 @@ def _loss_workspace() -> torch.Tensor:
     return torch.empty(int(n), dtype=torch.uint8, device=ops.require_cuda())
 
 
+@device_scoped
 def fogloss_raw(logits: torch.Tensor, labels: torch.Tensor, fog_density: Optional[torch.Tensor],
                 depth_pred: Optional[torch.Tensor], depth_tgt: Optional[torch.Tensor],
                 fog_sensitivity: float, focal: bool, want_grads: bool, want_dfog: bool = False):
@@ -48,6 +49,7 @@ def fogloss_raw(logits: torch.Tensor, labels: torch.Tensor, fog_density: Optiona
     return sums, dlogits, ddepth, bad, dfog
 
 
+@device_scoped
 def scale_inplace(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """x *= scale (device scalar fp32) through awx_scale_inplace."""
     lib = _lib.load()
@@ -100,6 +102,7 @@ class _DepthDensityFn(torch.autograd.Function):
     """fog density estimated from a predicted depth map (model.py:644-677): awx_depth_density_fwd / _bwd."""
 
     @staticmethod
+    @device_scoped
     def forward(ctx, depth):
         lib = _lib.load()
         d = ops.to_device(depth.detach(), torch.float32)
@@ -114,6 +117,7 @@ class _DepthDensityFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @device_scoped
     def backward(ctx, g):
         lib = _lib.load()
         (d,) = ctx.saved_tensors

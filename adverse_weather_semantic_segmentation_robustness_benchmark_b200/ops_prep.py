@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ops import _ptr, _stream, label_code, normalise_labels, require_cuda, to_device
+from .ops import _ptr, _stream, device_scoped, label_code, normalise_labels, require_cuda, to_device
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
@@ -27,6 +27,7 @@ def normalize_params(mean: Sequence[float], std: Sequence[float], max_pixel_valu
     return np.ascontiguousarray(m), np.ascontiguousarray(np.reciprocal(s, dtype=np.float32))
 
 
+@device_scoped
 def normalize_chw(images: torch.Tensor, mean: Sequence[float] = IMAGENET_MEAN, std: Sequence[float] = IMAGENET_STD,
                   max_pixel_value: float = 255.0, out_dtype: torch.dtype = torch.float32,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -51,6 +52,7 @@ def normalize_chw(images: torch.Tensor, mean: Sequence[float] = IMAGENET_MEAN, s
 STYLE = {"fog": (0.8, 30.0, None), "rain": (1.2, -10.0, 1.1), "snow": (0.9, 20.0, None), "night": (0.4, -20.0, 1.3)}
 
 
+@device_scoped
 def style_transfer(images: torch.Tensor, weather_type: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cv2.convertScaleAbs(alpha, beta) + blue-channel gain on uint8 [...,3] frames (loader.py:364-385)."""
     lib = _lib.load()
@@ -91,6 +93,7 @@ def lerp(a, b, t):
     return r
 
 
+@device_scoped
 def fog_density_map(images: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
     """get_fog_density_map (preprocessing.py:250-288) for a batch: images [B,H,W,3] (uint8, or float in
     [0,1] as the reference's signature says), depth [B,H,W] fp64/fp32 -> fog density [B,H,W] (depth's dtype).
@@ -124,6 +127,7 @@ def fog_density_map(images: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@device_scoped
 def local_contrast(images: torch.Tensor) -> torch.Tensor:
     """The fp32 [B,H,W] contrast map alone (intermediate of fog_density_map)."""
     lib = _lib.load()
@@ -138,6 +142,7 @@ def local_contrast(images: torch.Tensor) -> torch.Tensor:
     return contrast
 
 
+@device_scoped
 def estimate_depth(images: torch.Tensor, weights: np.ndarray) -> torch.Tensor:
     """DepthEstimationPreprocessor._geometric_depth_estimation (preprocessing.py:332-367): uint8 [B,H,W,3]
     -> fp64 [B,H,W].  `weights`: scipy's sigma=2 Gaussian taps (host, fp64)."""
@@ -157,6 +162,7 @@ def estimate_depth(images: torch.Tensor, weights: np.ndarray) -> torch.Tensor:
     return out
 
 
+@device_scoped
 def temperature_nll(logits: torch.Tensor, targets: torch.Tensor, temperatures: torch.Tensor, ignore_index: int = 255):
     """Sum over valid rows of cross_entropy(rows / T) for every T of the grid, in one pass.
     rows = logits.view(-1, C) exactly as the reference flattens (metrics.py:305).  Returns

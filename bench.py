@@ -14,10 +14,10 @@ all_reduce of the packed int64 bins closes the step.  One JSON line is printed b
             D2H of the bins inside the timed region
   roofline  awx_score (the dominant kernel): 153 algorithmic B/px x pixels per launch / mean launch
             time (CUDA events on the launching stream, inside the timed region) vs the measured copy peak
-  cpu_baseline  the oracle port (NumPy/OpenCV/SciPy/torch-CPU restatement of the reference) on one
-            frame per condition, timed on this box's host cores (rank 0, N=1 only)
---impl reference times that CPU port alone (the reference itself is Python and cannot travel to the
-GPU box; oracle/ is its checked restatement, see oracle/__init__.py).
+  cpu_baseline  the REFERENCE's own hot-path code (oracle/_ref: its three modules byte-compiled by
+            oracle/build_ref.py; the oracle port only if that is missing) on 2 full frames per condition,
+            timed on this box's host cores (rank 0, N=1 only)
+--impl reference times that CPU implementation alone, on full-size frames.
 """
 
 from __future__ import annotations
@@ -42,7 +42,7 @@ METRIC = "Mpixel/s fused corrupt->ensemble->mIoU/ECE eval"
 RAW_WEIGHTS = (0.3, 0.9)
 TEMPERATURE = 1.7
 AUROC_BINS = 4096
-POOL = 4                             # distinct host-drawn parameter sets per condition
+POOL = 64                            # distinct host-drawn parameter sets per condition (a pool of 64 per rank)
 
 
 def parse_args():
@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--sweep-frames", type=int, default=0,
                     help="BASELINE configs[4]: evaluation sweep over this many frames in total (e.g. 10000), sharded "
                          "over the ranks, one all_reduce at the end; prints its own JSON line and exits")
+    ap.add_argument("--pool", type=int, default=POOL, help="host-drawn corruption parameter sets per condition")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] side measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -124,73 +126,95 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------- CPU port (reference arm)
-def cpu_sample_inputs(h, w, seed=0):
+# ------------------------------------------------------------------- CPU arm (the reference itself)
+def cpu_sample_inputs(h, w, n_frames=1, seed=0):
+    """`n_frames` synthetic frames the way the reference's synthetic dataset makes them (loader.py:206,231) plus two
+    members' logits each (torch.randn, conftest.py:188,200)."""
     import numpy as np
     import torch
-    rng = np.random.RandomState(seed)
-    img = rng.randint(0, 255, (h, w, 3)).astype(np.uint8)
-    lab = torch.from_numpy(rng.randint(0, NUM_CLASSES, (1, h, w)).astype(np.uint8))
-    gen = torch.Generator().manual_seed(42 + seed)
-    la = torch.randn(1, NUM_CLASSES, h, w, generator=gen)
-    lb = torch.randn(1, NUM_CLASSES, h, w, generator=gen)
-    return img, lab, la, lb
+    frames = []
+    for i in range(n_frames):
+        rng = np.random.RandomState(seed + i)
+        img = rng.randint(0, 255, (h, w, 3)).astype(np.uint8)
+        lab = torch.from_numpy(rng.randint(0, NUM_CLASSES, (1, h, w)).astype(np.uint8))
+        gen = torch.Generator().manual_seed(42 + seed + i)
+        frames.append((img, lab, torch.randn(1, NUM_CLASSES, h, w, generator=gen),
+                       torch.randn(1, NUM_CLASSES, h, w, generator=gen)))
+    return frames
 
 
-def cpu_step(inputs) -> float:
-    """One frame per condition through the oracle port: corrupt + fuse + the reference's
+def cpu_kind():
+    """'reference': oracle/_ref holds the reference's own byte-compiled hot-path modules (oracle/build_ref.py, built
+    where /root/reference exists and shipped with the snapshot); 'port': only the oracle restatement is available."""
+    from oracle import reference as oref
+    return "reference" if oref.available() else "port"
+
+
+def cpu_step(frames) -> float:
+    """Every frame through every condition on the host: corrupt + fuse + the reference's
     compute_comprehensive_metrics set (IoU, accuracy, ECE, disagreement AUROC).  Returns pixels."""
     import numpy as np
     import torch
+    from oracle import reference as oref
+    if oref.available():     # the reference's own code (apply_weather_effect / EnsembleModel.forward / RobustnessMetrics)
+        return oref.reference_step(frames, CONDITIONS, RAW_WEIGHTS, TEMPERATURE, NUM_CLASSES)
     from oracle import weather as ow, fusion as of_, metrics as om
-    img, lab, la, lb = inputs
     raw_w = torch.tensor(RAW_WEIGHTS)
     temp = torch.tensor([TEMPERATURE])
     np.random.seed(42)
+    px = 0.0
     for kind in CONDITIONS:
-        ow.apply(img, kind)
-        fused = of_.fuse_logits(la, lb, "weighted_average", raw_w, temp)
-        om.iou(fused, lab, NUM_CLASSES)
-        om.pixel_accuracy(fused, lab)
-        om.ece(fused, lab)
-        om.disagreement_auroc([la, lb], lab)
-    return float(len(CONDITIONS) * img.shape[0] * img.shape[1])
+        for img, lab, la, lb in frames:
+            ow.apply(img, kind)
+            fused = of_.fuse_logits(la, lb, "weighted_average", raw_w, temp)
+            om.iou(fused, lab, NUM_CLASSES)
+            om.pixel_accuracy(fused, lab)
+            om.ece(fused, lab)
+            om.disagreement_auroc([la, lb], lab)
+            px += float(img.shape[0] * img.shape[1])
+    return px
+
+
+def cpu_sample_text(n_frames, h, w):
+    return (f"{n_frames} full {h}x{w} frame(s) per condition x {len(CONDITIONS)} conditions per step: "
+            "apply_weather_effect + EnsembleModel fusion + compute_comprehensive_metrics (IoU / accuracy / ECE / AUROC)")
 
 
 def run_reference_arm(args, rank):
+    """The reference's CPU implementation of the path on this box's host cores, FULL-SIZE frames: 2 per condition
+    per step when the whole --steps / --warmup run then fits ~5 minutes, else 1."""
     import torch
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    # bound the whole run to a few minutes: probe the CPU speed on 1/8 of the rows, then keep as many
-    # rows of each frame as fit the budget (full frames when they do)
-    budget_s = 150.0
-    probe_rows = max(8, args.height // 8)
+    kind = cpu_kind()
+    budget_s = 300.0
+    one = cpu_sample_inputs(args.height, args.width, 1)
+    cpu_step(cpu_sample_inputs(max(32, args.height // 16), args.width, 1))   # imports, thread pools
     t0 = time.perf_counter()
-    cpu_step(cpu_sample_inputs(probe_rows, args.width))
-    est_full = (time.perf_counter() - t0) * args.height / probe_rows
+    cpu_step(one)
+    t_frame = time.perf_counter() - t0
     total_steps = max(args.steps + args.warmup, 1)
-    rows = args.height
-    if est_full * total_steps > budget_s:
-        rows = int(max(64, min(args.height, args.height * budget_s / (est_full * total_steps))))
-        rows -= rows % 8
-    inputs = cpu_sample_inputs(rows, args.width)
+    n_frames = 2 if 2 * t_frame * total_steps <= budget_s else 1
+    frames = cpu_sample_inputs(args.height, args.width, n_frames)
     for _ in range(args.warmup):
-        cpu_step(inputs)
+        cpu_step(frames)
     t0 = time.perf_counter()
     px = 0.0
     for _ in range(args.steps):
-        px += cpu_step(inputs)
+        px += cpu_step(frames)
     dt = time.perf_counter() - t0
     value = px / dt / 1e6
-    sample = (f"1 frame per condition ({len(CONDITIONS)} frames), {rows} of {args.height} rows x {args.width} "
-              f"per step: corrupt + fuse + IoU/accuracy/ECE/AUROC")
+    # `config` is the GPU arm's (the driver pairs the two lines on it); what THIS arm ran per step -- full-size frames,
+    # fewer of them -- is stated in `sample` / `cpu_baseline.sample`
+    cfg = workload_config(args)
+    sample = cpu_sample_text(n_frames, args.height, args.width)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
+        "config": cfg, "sample": sample, "frames_per_condition_per_step": n_frames,
+        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -224,7 +248,9 @@ class Workload:
         self.args = args
         b, h, w = args.batch, args.height, args.width
         self.b, self.h, self.w = b, h, w
-        gen = torch.Generator(device=device).manual_seed(42 + 1000 * rank)
+        # the same synthetic frames on every rank (seeded by content, not by rank): weak scaling does not care, and
+        # the sharded sweep / probe results are then comparable across world sizes bit for bit
+        gen = torch.Generator(device=device).manual_seed(42)
         self.la = torch.randn(b, NUM_CLASSES, h, w, device=device, generator=gen)
         self.lb = torch.randn(b, NUM_CLASSES, h, w, device=device, generator=gen)
         # images / labels the way the reference's synthetic dataset makes them (loader.py:206,231)
@@ -232,21 +258,31 @@ class Workload:
         self.labels = torch.randint(0, NUM_CLASSES, (b, h, w), device=device, generator=gen, dtype=torch.uint8)
         self.out = torch.empty_like(self.images)
         self.workspace = ops.corrupt_workspace(b, h, w)
-        # host draws with the reference's RNG and order, from a pool of POOL parameter sets per
-        # condition cycled over the batch (drawing 64 fog+night fields costs ~30 s of host time)
-        t = WeatherDegradationTransforms(seed=42 + rank)
+        # host draws with the reference's RNG and order: a pool of `--pool` parameter sets per condition, cycled over
+        # the batch; fog / night fields are uploaded slot by slot (a slot's host arrays are dropped at once)
+        t = WeatherDegradationTransforms(seed=42)
         self.params, self.fields, self.items = {}, {}, {}
-        pool = min(POOL, b)
+        pool = max(1, min(args.pool, b))
         for kind in CONDITIONS[1:]:
-            draws = [t.draw(kind, h, w) for _ in range(pool)]
+            draws = []
+            fld = None
             if kind == "fog":
-                depth = t.synthetic_depth(np.stack([d.depth_noise for d in draws]))  # device fp64 [pool,H,W]
-                fld = depth.repeat((b + pool - 1) // pool, 1, 1)[:b].contiguous().reshape(-1)
+                fld = torch.empty((b, h, w), dtype=torch.float64, device=device)
             elif kind == "night":
-                nz = torch.from_numpy(np.stack([d.noise for d in draws])).to(device)
-                fld = nz.repeat((b + pool - 1) // pool, 1, 1, 1)[:b].contiguous().reshape(-1)
-            else:
-                fld = None
+                fld = torch.empty((b, h, w, 3), dtype=torch.float64, device=device)
+            for i in range(pool):
+                d = t.draw(kind, h, w)
+                if kind == "fog":
+                    fld[i] = t.synthetic_depth(d.depth_noise[None])[0]     # device fp64 [H,W]
+                    d.depth_noise = None
+                elif kind == "night":
+                    fld[i] = torch.from_numpy(d.noise).to(device)
+                    d.noise = None
+                draws.append(d)
+            if fld is not None:
+                for i in range(pool, b):
+                    fld[i] = fld[i % pool]
+                fld = fld.reshape(-1)
             full = [draws[i % pool] for i in range(b)]
             prm, _, items = t.pack(full, h, w, gather_fields=False)  # fields are assembled on the device
             self.params[kind] = prm
@@ -266,17 +302,21 @@ class Workload:
         fields = self.fields if fields is None else fields
         self.ev.reset()  # a step is one sweep: score -> all_reduce -> (finalise); the merged bins are the step's result
         for kind in CONDITIONS:
-            if kind != "clean":   # 'clean' aliases its input in the reference (preprocessing.py:78-79)
-                ops.corrupt(images, self.params[kind], fields[kind], self.items[kind], out=self.out,
-                            workspace=self.workspace)
-            if self.record_score_events:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                self.ev.update(kind, la, lb, labels)
-                e1.record()
-                self.score_events.append((e0, e1))
+            if kind == "clean":
+                # 'clean' aliases its input in the reference (preprocessing.py:78-79): a bare score launch, which is
+                # also the one the roofline times (the other four are the same launch behind their corruption kernels,
+                # inside ONE C call each -- awx_corrupt_score -- where no event can be placed between the two)
+                if self.record_score_events:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    self.ev.update(kind, la, lb, labels)
+                    e1.record()
+                    self.score_events.append((e0, e1))
+                else:
+                    self.ev.update(kind, la, lb, labels)
             else:
-                self.ev.update(kind, la, lb, labels)
+                self.ev.update_corrupted(kind, images, self.params[kind], fields[kind], self.items[kind], self.out,
+                                         self.workspace, la, lb, labels)
         self.ev.all_reduce()
 
 
@@ -355,17 +395,22 @@ def run_gpu_arm(args, rank, world, local_rank):
         if near_cpus is not None:
             e2e["cpu_affinity"] = "rank pinned to the %d CPUs NVML reports closest to its GPU" % near_cpus
 
-    # ---- CPU baseline (rank 0, N=1 only)
+    # ---- CPU baseline (rank 0, N=1 only): the reference's own code on 2 full frames per condition
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
-        inputs = cpu_sample_inputs(args.height, args.width)
+        cpu_step(cpu_sample_inputs(max(32, args.height // 16), args.width, 1))    # imports, thread pools
+        frames = cpu_sample_inputs(args.height, args.width, 2)
         t0 = time.perf_counter()
-        px = cpu_step(inputs)
+        px = cpu_step(frames)
         dt = time.perf_counter() - t0
-        cpu = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"1 frame per condition ({len(CONDITIONS)} frames) at {args.height}x{args.width}, "
-                         f"corrupt + fuse + IoU/accuracy/ECE/AUROC, {dt:.1f} s"}
+        cpu = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": cpu_kind(),
+               "sample": cpu_sample_text(2, args.height, args.width) + f", {dt:.1f} s"}
+
+    configs = None
+    if not args.no_configs:
+        configs = configs_object(wl, args, rank, world, barrier, max_over_ranks)
+    shard_ok, shard_digest = sharding_probe(wl, args, rank, world, device)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -384,86 +429,200 @@ def run_gpu_arm(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(args),
-            "roofline": {"bound": "hbm", "kernel": "score_v2_kernel<weighted,u8 labels,bins only> (awx_score)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "score_v2_kernel<weighted,u8 labels,bins only> (awx_score)", "timed_launch": "the clean condition's launch of every timed step (the four others run the same kernel behind their corruption kernels inside awx_corrupt_score)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": SCORE_BYTES_PER_PX * px_launch,
                          "ms_per_launch": score_ms,
                          "whole_step_GBps": step_bytes / (ms_step * 1e-3) / 1e9},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "parity": parity_object(wl, results, world),
+            "configs": configs,
         }
+        line["parity"]["sharded_bins_equal_single"] = shard_ok
+        line["parity"]["sharding_probe"] = ("16 frames of %dx%d, frame i -> rank i mod %d, all_reduce vs all 16 on rank 0; "
+                                            "bins sha256 %s" % (args.height, args.width, world, shard_digest))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def sweep_blocks(total_frames, batch, rank, world):
+    """BASELINE configs[4] sharding: the sweep is cut into blocks of `batch` consecutive frames; block k goes to
+    rank k mod world and is evaluated under condition k mod 5.  Every block is the rank's (rank-independent) pool of
+    frames, so the merged bins depend on the total number of frames only -- not on the number of ranks."""
+    n_blocks = (total_frames + batch - 1) // batch
+    return [(k, min(batch, total_frames - k * batch)) for k in range(n_blocks) if k % world == rank]
+
+
+def run_one_sweep(wl, blocks):
+    wl.ev.reset()
+    for k, n in blocks:
+        kind = CONDITIONS[k % len(CONDITIONS)]
+        if kind == "clean":
+            wl.ev.update(kind, wl.la[:n], wl.lb[:n], wl.labels[:n])
+        else:
+            wl.ev.update_corrupted(kind, wl.images[:n], wl.params[kind][:n], wl.fields[kind], wl.items[kind], wl.out[:n],
+                                   wl.workspace, wl.la[:n], wl.lb[:n], wl.labels[:n])
+    wl.ev.all_reduce()       # ONE collective closes the sweep
+
+
+def bins_digest(ev):
+    import hashlib
+    return hashlib.sha256(ev.canonical_bins().cpu().numpy().tobytes()).hexdigest()[:16]
+
+
+def measure_sweep(wl, args, frames, rank, world, barrier, max_over_ranks):
+    """One warm-up sweep, one timed sweep (CUDA events, max over ranks).  Strong scaling: `frames` is the total."""
+    import torch
+    blocks = sweep_blocks(frames, args.batch, rank, world)
+    lib = wl.lib
+    run_one_sweep(wl, blocks)
+    barrier()
+    launches0 = lib.awx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_one_sweep(wl, blocks)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    res = wl.ev.finalize()
+    px = float(frames) * args.height * args.width
+    step_bytes = sum((SCORE_BYTES_PER_PX + CORRUPT_BYTES_PER_PX[CONDITIONS[k % 5]]) * n * args.height * args.width
+                     for k, n in sweep_blocks(frames, args.batch, 0, 1))
+    peak, _ = measured_peak()
+    return {"frames": frames, "ms": ms, "frames_per_s": frames / (ms * 1e-3), "Mpixel_per_s": px / (ms * 1e-3) / 1e6,
+            "GBps_all_gpus": step_bytes / (ms * 1e-3) / 1e9, "frac_of_measured_peak_per_gpu": step_bytes / (ms * 1e-3) / 1e9 / peak / world,
+            "gpu_launches_this_rank": int(lib.awx_launch_count() - launches0), "blocks_this_rank": len(blocks),
+            "bins_sha256_16": bins_digest(wl.ev),
+            "results": {k: (float(v) if v == v else None) for k, v in res.items()}}
+
+
 def run_sweep(args, rank, world, local_rank):
-    """BASELINE configs[4]: N frames in total, frame i -> rank i mod world (batches of --batch frames cycled from
-    the rank's pool of pre-drawn frames / parameters), every batch corrupted under one condition (cycling through
-    the five) and scored into that condition's bins; ONE all_reduce of the packed bins closes the sweep.
-    Strong scaling: the total number of frames is fixed."""
+    """BASELINE configs[4] as its own run: `--sweep-frames N` frames in total, sharded by block over the ranks, one
+    all_reduce of the packed bins at the end.  `bins_sha256_16` / `results` must not depend on the number of ranks."""
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import _lib
-    lib = _lib.load()
     wl = Workload(args, rank, device)
-    mine = len(range(rank, args.sweep_frames, world))
-    batches = [(args.batch if (i + 1) * args.batch <= mine else mine - i * args.batch)
-               for i in range((mine + args.batch - 1) // args.batch)]
-
-    def sweep():
-        wl.ev.reset()
-        for i, nb in enumerate(batches):
-            kind = CONDITIONS[i % len(CONDITIONS)]
-            if kind != "clean":
-                wl.ops.corrupt(wl.images[:nb], wl.params[kind][:nb], wl.fields[kind], wl.items[kind], out=wl.out[:nb],
-                               workspace=wl.workspace)
-            wl.ev.update(kind, wl.la[:nb], wl.lb[:nb], wl.labels[:nb])
-        wl.ev.all_reduce()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    sweep()  # warm-up
-    barrier()
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = lib.awx_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    sweep()
-    e1.record()
-    barrier()
-    launches = lib.awx_launch_count() - launches0
+    m = measure_sweep(wl, args, args.sweep_frames, rank, world, barrier, max_over_ranks)
     clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    res = wl.ev.finalize()
     if rank == 0:
-        px = float(args.sweep_frames) * args.height * args.width
         cfg = workload_config(args)
-        cfg["workload"] = ("configs[4]: %d-frame synthetic Cityscapes eval sweep, frame i -> rank i mod %d, batches of %d "
-                           "frames cycled from a per-rank pool, one condition per batch, one all_reduce of the bins"
-                           % (args.sweep_frames, world, args.batch))
+        cfg["workload"] = ("configs[4]: %d-frame synthetic Cityscapes eval sweep in blocks of %d frames, block k -> rank k mod %d "
+                           "under condition k mod 5, one all_reduce of the bins" % (args.sweep_frames, args.batch, world))
         print(json.dumps({
-            "metric": METRIC, "value": px / (ms * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": 1, "warmup": 1,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32",
-            "data": "synthetic", "config": cfg, "frames": args.sweep_frames, "frames_per_s": args.sweep_frames / (ms * 1e-3),
-            "gpu_launches": int(launches), "clocks": clocks,
-            "results": {k: (float(v) if v == v else None) for k, v in res.items()},
-            "bins_checksum": int(wl.ev.bins.sum().item())}), flush=True)
+            "metric": METRIC, "value": m["Mpixel_per_s"], "unit": "Mpixel/s", "n_gpus": world, "steps": 1, "warmup": 1,
+            "ms_per_step": m["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32",
+            "data": "synthetic", "config": cfg, "frames": args.sweep_frames, "frames_per_s": m["frames_per_s"],
+            "gpu_launches": m["gpu_launches_this_rank"], "clocks": clocks, "results": m["results"],
+            "bins_sha256_16": m["bins_sha256_16"]}), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_launches(fn, n=10):
+    """Median CUDA-event time (ms) of `n` individually bracketed calls on the current stream, after 3 warm-ups."""
+    import torch
+    for _ in range(3):
+        fn()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for e0, e1 in ev:
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    return t[len(t) // 2]
+
+
+def configs_object(wl, args, rank, world, barrier, max_over_ranks):
+    """BASELINE configs[2..4] beside the headline (configs[1]): CUDA-event timings on this rank's GPU with the same
+    library, so that the loss kernel's and the sweep's numbers are driver-visible.
+      c2_fusion_frame  one 19x1024x2048 frame per member: fuse (weighted, /T) + softmax + JS map + ECE + AUROC, the
+                       fused logits and the JS map materialised (153 B/px read + 80 written)
+      c3_loss_fwd_bwd  fog-density-aware loss forward + backward, batch 8, depth prediction + target, int64 labels
+                       (176 B/px)
+      c4_sweep         the 10 000-frame sweep sharded over the ranks (total frames fixed: strong scaling)"""
+    import torch
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops_loss
+    peak, _ = measured_peak()
+    h, w = args.height, args.width
+    ev = wl.ev
+    out = {}
+    bins2 = wl.ops.new_bins(NUM_CLASSES, 15, AUROC_BINS)
+    px2 = float(h * w)
+    ms = time_launches(lambda: wl.ops.score(wl.la[:1], wl.lb[:1], wl.labels[:1], strategy=ev.strategy, w0=ev.w0, w1=ev.w1,
+                                            temperature=ev.temperature, auroc_bins=AUROC_BINS, bins=bins2,
+                                            want_fused=True, want_js=True))
+    out["c2_fusion_frame"] = {"ms": ms, "bytes_per_px": 233.0, "GBps": 233.0 * px2 / (ms * 1e-3) / 1e9,
+                              "frac_of_measured_peak": 233.0 * px2 / (ms * 1e-3) / 1e9 / peak,
+                              "note": "2 Mpx launch: 148 CTAs x 29 tiles, launch + tail bound; fused logits + JS map written"}
+    nb = min(8, args.batch)
+    gen = torch.Generator(device=wl.la.device).manual_seed(7)
+    lab64 = wl.labels[:nb].long()
+    fd = torch.rand(nb, h, w, device=wl.la.device, generator=gen)
+    dpred = torch.rand(nb, 1, h, w, device=wl.la.device, generator=gen) * 50
+    dtgt = torch.rand(nb, h, w, device=wl.la.device, generator=gen) * 50
+    px3 = float(nb * h * w)
+    ms = time_launches(lambda: ops_loss.fogloss_raw(wl.la[:nb], lab64, fd, dpred, dtgt, 2.0, False, True))
+    out["c3_loss_fwd_bwd"] = {"ms": ms, "batch": nb, "bytes_per_px": 176.0, "GBps": 176.0 * px3 / (ms * 1e-3) / 1e9,
+                              "frac_of_measured_peak": 176.0 * px3 / (ms * 1e-3) / 1e9 / peak,
+                              "note": "includes the wrapper's output allocations; kernel: fogloss_ring_kernel"}
+    del fd, dpred, dtgt, lab64
+    m = measure_sweep(wl, args, 10000, rank, world, barrier, max_over_ranks)
+    m.pop("results")
+    out["c4_sweep"] = m
+    return out
+
+
+def sharding_probe(wl, args, rank, world, device):
+    """On-hardware proof that sharded bins do not depend on the number of ranks: a fixed probe of 16 full-size frames
+    (content seeded by the frame's index, condition = index mod 5) is scored with frame i on rank i mod world and
+    merged by the all_reduce; rank 0 also scores all 16 alone.  The two buffers must be identical."""
+    import torch
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation.streaming import StreamingEvaluator
+    h, w = args.height, args.width
+    ev = wl.ev
+    make = lambda: StreamingEvaluator(NUM_CLASSES, CONDITIONS, 15, AUROC_BINS, "weighted_average", RAW_WEIGHTS,
+                                      TEMPERATURE, ensemble=True, bins_device=device)
+    shard, single = make(), make()
+
+    def frame(i):
+        gen = torch.Generator(device=device).manual_seed(7000 + i)
+        la = torch.randn(1, NUM_CLASSES, h, w, device=device, generator=gen)
+        lb = torch.randn(1, NUM_CLASSES, h, w, device=device, generator=gen)
+        lab = torch.randint(0, NUM_CLASSES, (1, h, w), device=device, generator=gen, dtype=torch.uint8)
+        lab[0, : 1 + i % 3] = 255
+        return la, lb, lab
+
+    for i in range(16):
+        if i % world == rank or rank == 0:
+            la, lb, lab = frame(i)
+            if i % world == rank:
+                shard.update(CONDITIONS[i % 5], la, lb, lab)
+            if rank == 0:
+                single.update(CONDITIONS[i % 5], la, lb, lab)
+    shard.all_reduce()
+    return bool(torch.equal(shard.canonical_bins(), single.canonical_bins())), bins_digest(single)
 
 
 def parity_object(wl, results, world):
@@ -575,10 +734,11 @@ def run_e2e(args, wl, device, world, barrier, max_over_ranks, px_step):
             sl = slice(k * cb, (k + 1) * cb)
             main.wait_event(ready[k])
             for kind in CONDITIONS:
-                if kind != "clean":
-                    wl.ops.corrupt(d_images[sl], wl.params[kind][sl], d_fields[kind], wl.items[kind], out=wl.out[sl],
-                                   workspace=wl.workspace)
-                wl.ev.update(kind, d_la[sl], d_lb[sl], d_labels[sl])
+                if kind == "clean":
+                    wl.ev.update(kind, d_la[sl], d_lb[sl], d_labels[sl])
+                else:
+                    wl.ev.update_corrupted(kind, d_images[sl], wl.params[kind][sl], d_fields[kind], wl.items[kind],
+                                           wl.out[sl], wl.workspace, d_la[sl], d_lb[sl], d_labels[sl])
             done[k].record(main)
         wl.ev.all_reduce()
         return wl.ev.bins.cpu()      # D2H read of the step's result
@@ -594,6 +754,31 @@ def run_e2e(args, wl, device, world, barrier, max_over_ranks, px_step):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+
+    # the same copies with no kernel behind them: if the step takes what its copies alone take, the leg is bound by
+    # the host -> device path (PCIe link at N = 1, the host's memory / IO fabric when several ranks copy at once)
+    def copies_only():
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            for k in range(n_chunks):
+                sl = slice(k * cb, (k + 1) * cb)
+                d_images[sl].copy_(h_images[sl], non_blocking=True)
+                d_labels[sl].copy_(h_labels[sl], non_blocking=True)
+                d_la[sl].copy_(h_la[sl], non_blocking=True)
+                d_lb[sl].copy_(h_lb[sl], non_blocking=True)
+                for kind, v in h_fields.items():
+                    if v is not None:
+                        fs = slice(k * cb * per_frame[kind], (k + 1) * cb * per_frame[kind])
+                        d_fields[kind][fs].copy_(v[fs], non_blocking=True)
+        main.wait_stream(copy_stream)
+
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    copies_only()
+    c1.record()
+    barrier()
+    copy_ms = max_over_ranks(c0.elapsed_time(c1))
     # the pipelined, chunked step must produce exactly the (merged) bins of one plain device-resident step
     got = wl.ev.canonical_bins()
     wl.ev.reset()
@@ -602,7 +787,11 @@ def run_e2e(args, wl, device, world, barrier, max_over_ranks, px_step):
     bins_match = bool(torch.equal(got, wl.ev.canonical_bins()))
     return {"value": world * px_step / (ms * 1e-3) / 1e6, "bins_match_device_resident_step": bins_match, "unit": "Mpixel/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": ms, "steps": steps, "pinned": pinned,
-            "api": "ops.corrupt + StreamingEvaluator.update (awx_corrupt / awx_score via the C ABI)",
+            "h2d_GBps_per_gpu": h2d / (ms * 1e-3) / 1e9, "h2d_GBps_all_gpus": world * h2d / (ms * 1e-3) / 1e9,
+            "copies_only_ms": copy_ms, "copies_only_GBps_per_gpu": h2d / (copy_ms * 1e-3) / 1e9,
+            "bound": ("host->device copies (the step takes %.2fx what its copies alone take; tools/h2d_probe.py, "
+                      "profiles/r2_h2d_probe_*.json)" % (ms / copy_ms)) if ms < 1.25 * copy_ms else "compute",
+            "api": "StreamingEvaluator.update_corrupted (awx_corrupt_score via the C ABI; 'clean': update / awx_score)",
             "pipeline": "%d chunks of %d frames: H2D on a copy stream overlapped with corrupt + score" % (n_chunks, cb)}
 
 

@@ -106,9 +106,10 @@ typedef struct AwxScoreMaps {
  *   ece_correct[nb]       of those, pred == target
  *   ece_conf_hi[nb], ece_conf_lo[nb]   sum of conf in 2^-31 fixed point = hi*2^32 + lo; both words are plain
  *                          accumulators (lo may exceed 2^32), so equal sums need not be equal word by word
- *   auroc_pos  [NB], auroc_neg[NB]     MI histogram of wrong / right ensemble pixels
- *   counters   [AWX_NUM_COUNTERS]  AWX_CNT_*                                          */
-typedef struct AwxBinsLayout {
+ *   counters   [AWX_NUM_COUNTERS]  AWX_CNT_*
+ *   auroc_pos  [NB], auroc_neg[NB]     MI histogram of wrong / right ensemble pixels; last, so that the layout
+ *                          for NB = 0 is a prefix of the layout for any NB                 */
+typedef struct AwxBinsLayout { /* word offsets; the field order of this struct is not the memory order */
   int64_t confusion, ece_count, ece_correct, ece_conf_hi, ece_conf_lo;
   int64_t auroc_pos, auroc_neg, counters, total_words;
 } AwxBinsLayout;

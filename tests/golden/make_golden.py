@@ -327,6 +327,92 @@ def trainer_cases():
     np.savez_compressed(os.path.join(HERE, "trainer.npz"), **out)
 
 
+def evaluate_batches(seed, n_batches, bsz, c, h, w, label_dtype, with_other):
+    """Synthetic test loader with the member logits of every batch stashed next to it."""
+    gen = torch.Generator().manual_seed(seed)
+    rng = np.random.RandomState(seed)
+    names = ["clean", "fog", "rain", "snow", "night"] + (["hail"] if with_other else [])
+    batches = []
+    for _ in range(n_batches):
+        lab = torch.randint(0, c, (bsz, h, w), generator=gen)
+        lab[torch.rand(bsz, h, w, generator=gen) < 0.03] = 255
+        batches.append({"image": torch.zeros(bsz, 3, 4, 4),
+                        "label": lab.to(label_dtype),
+                        "weather_condition": [names[i] for i in rng.randint(0, len(names), bsz)],
+                        "_la": torch.randn(bsz, c, h, w, generator=gen) * 2,
+                        "_lb": torch.randn(bsz, c, h, w, generator=gen) * 2})
+    batches[0]["weather_condition"][0] = "clean"   # the degradation ratios need a clean frame
+    return batches
+
+
+def evaluate_cases():
+    """the reference's OWN evaluate_model (scripts/evaluate.py:134-274) run on its OWN
+    EnsembleModel (trained-looking fusion weights, temperature != 1) with two replaying members injected, on
+    loaders with int64 / uint8 labels, mixed weather and a condition the config does not list; plus the same
+    model behind a DistributedDataParallel-style wrapper (the reference then finds no `segformer` attribute and
+    reports no ensemble AUROC) and a single-member model."""
+    ev = refshim.evaluate_script()
+    met = refshim.metrics()
+    out = {"versions": versions()}
+
+    class _Member(torch.nn.Module):
+        def __init__(self, batches, key):
+            super().__init__()
+            self.batches, self.key, self.i = batches, key, 0
+
+        def forward(self, x):
+            b = self.batches[self.i]
+            self.i += 1
+            return {"segmentation": b[self.key]}
+
+    class _Wrapper(torch.nn.Module):      # what DistributedDataParallel looks like from outside
+        def __init__(self, module):
+            super().__init__()
+            self.module = module
+
+        def forward(self, x):
+            return self.module(x)
+
+    class _Config:
+        def __init__(self, d):
+            self.d = d
+
+        def get(self, k, default=None):
+            return self.d.get(k, default)
+
+    conds = ["clean", "fog", "rain", "snow", "night"]
+    cases = {  # tag: (seed, batches, batch size, C, H, W, label dtype, other condition, strategy, T scaling, wrapped, single)
+        "e_weighted": (11, 4, 3, 19, 12, 16, torch.int64, True, "weighted_average", True, False, False),
+        "e_u8": (12, 3, 4, 19, 8, 20, torch.uint8, True, "weighted_average", True, False, False),
+        "e_maxconf": (13, 3, 3, 19, 12, 16, torch.int64, False, "max_confidence", True, False, False),
+        "e_mean_not": (14, 3, 3, 19, 12, 16, torch.int64, True, "mean", False, False, False),
+        "e_wrapped": (15, 3, 3, 19, 12, 16, torch.int64, True, "weighted_average", True, True, False),
+        "e_single": (16, 3, 3, 19, 12, 16, torch.int64, False, None, False, False, True),
+    }
+    for tag, (seed, nb, bsz, c, h, w, ldt, other, strategy, ts, wrapped, single) in cases.items():
+        batches = evaluate_batches(seed, nb, bsz, c, h, w, ldt, other)
+        if single:
+            model = _Member(batches, "_la")
+        else:
+            model = refshim.ensemble_with_fixed_members(batches[0]["_la"], batches[0]["_lb"], strategy, ts,
+                                                        raw_weights=torch.tensor([0.3, 0.9]),
+                                                        temperature=torch.tensor([1.7]))
+            model.segformer, model.deeplabv3plus = _Member(batches, "_la"), _Member(batches, "_lb")
+            if wrapped:
+                model = _Wrapper(model)
+        res = ev.evaluate_model(model, batches, met.RobustnessMetrics(c), torch.device("cpu"),
+                                _Config({"data.weather_conditions": conds}))
+        out[f"{tag}_args"] = np.array([seed, nb, bsz, c, h, w, int(other), int(ts), int(wrapped), int(single)])
+        out[f"{tag}_strategy"] = np.array(str(strategy))
+        out[f"{tag}_keys"] = np.array(sorted(res))
+        out[f"{tag}_vals"] = np.array([float(res[k]) for k in sorted(res)], dtype=np.float64)
+        for i, b in enumerate(batches):
+            for k, v in b.items():
+                if k != "image":
+                    out[f"{tag}_b{i}_{k}"] = np.array(v) if k == "weather_condition" else v.numpy()
+    np.savez_compressed(os.path.join(HERE, "evaluate.npz"), **out)
+
+
 if __name__ == "__main__":
     if not refshim.available():
         raise SystemExit("reference not present; golden files can only be regenerated in the build container")
@@ -336,6 +422,7 @@ if __name__ == "__main__":
     loss_cases()
     prep_cases()
     trainer_cases()
+    evaluate_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

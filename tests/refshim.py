@@ -85,6 +85,30 @@ def trainer():
     return _cache["trainer"]
 
 
+def evaluate_script():
+    """scripts/evaluate.py (the reference's evaluation driver) loaded by path.  Its plotting imports (matplotlib,
+    seaborn: not installed here, used only by generate_evaluation_report) are stubbed; everything
+    ``evaluate_model`` touches is the reference's own code."""
+    if "evaluate" not in _cache:
+        loader()
+        model()
+        for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):
+            if name not in sys.modules:
+                try:
+                    __import__(name)
+                except Exception:
+                    sys.modules[name] = types.ModuleType(name)
+        if "matplotlib" in sys.modules and not hasattr(sys.modules["matplotlib"], "pyplot"):
+            sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+        if "segmentation_models_pytorch" not in sys.modules:
+            sys.modules["segmentation_models_pytorch"] = types.ModuleType("segmentation_models_pytorch")
+        spec = importlib.util.spec_from_file_location("_awx_ref_evaluate", os.path.join(REF_ROOT, "scripts", "evaluate.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _cache["evaluate"] = mod
+    return _cache["evaluate"]
+
+
 def ensemble_with_fixed_members(l1, l2, strategy="weighted_average", temperature_scaling=True,
                                 raw_weights=None, temperature=None, d1=None, d2=None):
     """The reference's EnsembleModel with two tiny producers injected, so that its own

@@ -46,6 +46,7 @@ class _Ensemble(torch.nn.Module):
         super().__init__()
         self.batches, self.i = batches, 0
         self.ensemble_strategy, self.temperature_scaling = strategy, ts
+        self.segformer = torch.nn.Identity()   # evaluate.py:196: ensemble statistics only for models with this member
         self.ensemble_weights = torch.nn.Parameter(torch.tensor([0.3, 0.9]))
         self.temperature = torch.nn.Parameter(torch.tensor([1.7]))
 
@@ -113,6 +114,88 @@ def test_evaluate_model_ensemble(strategy, ts):
     exact = om.disagreement_auroc([torch.cat([b["_la"] for b in batches]), torch.cat([b["_lb"] for b in batches])], tg)
     assert abs(res["ensemble_disagreement_auroc"] - exact) <= 2e-3
     assert not any(k.startswith("miou___") or "hail" in k for k in res)
+
+
+class _DDPLike(torch.nn.Module):
+    """What DistributedDataParallel looks like from outside: the model sits in ``.module``."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, x):
+        return self.module(x)
+
+
+@pytest.mark.parametrize("tag", ["e_weighted", "e_u8", "e_maxconf", "e_mean_not", "e_wrapped", "e_single"])
+def test_evaluate_model_matches_a_run_of_the_reference(golden, tag):
+    """tests/golden/evaluate.npz holds result dicts of the REFERENCE's evaluate_model (scripts/evaluate.py:134-274)
+    on its own EnsembleModel with trained-looking fusion weights ([0.3, 0.9]) and temperature 1.7, int64 / uint8
+    labels, mixed weather, a condition the config does not list, the model behind a DDP-style wrapper, and a
+    single-member model.  The drop-in must return the same keys; mIoU and degradation ratios ==, ECE to 1e-5,
+    AUROC within the histogram bound."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import evaluate_model
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import EnsembleModel, RobustnessMetrics
+    from trainer_fixture import evaluate_fixture_batches, ReplayMember
+    g = golden("evaluate")
+    _, _, _, c, _, _, _, ts, wrapped, single = (int(x) for x in g[f"{tag}_args"])
+    batches = evaluate_fixture_batches(g, tag)
+    dev = torch.device("cuda")
+    if single:
+        model = ReplayMember(batches, "_la", dev)
+    else:
+        model = EnsembleModel(num_classes=c, include_depth=False, ensemble_strategy=str(g[f"{tag}_strategy"]),
+                              temperature_scaling=bool(ts), segformer=ReplayMember(batches, "_la", dev),
+                              deeplabv3plus=ReplayMember(batches, "_lb", dev))
+        with torch.no_grad():
+            model.ensemble_weights.copy_(torch.tensor([0.3, 0.9]))
+            if ts:
+                model.temperature.copy_(torch.tensor([1.7]))
+        model = model.to(dev)
+        if wrapped:
+            model = _DDPLike(model)
+    res = evaluate_model(model, batches, RobustnessMetrics(c), dev, _Config({"data.weather_conditions": CONDS}))
+    want = dict(zip((str(k) for k in g[f"{tag}_keys"]), g[f"{tag}_vals"]))
+    assert sorted(res) == sorted(want)
+    for k, v in want.items():
+        if k.startswith("ece") or k == "expected_calibration_error":
+            np.testing.assert_allclose(res[k], v, rtol=1e-5, atol=1e-8, err_msg=k)
+        elif k == "ensemble_disagreement_auroc":
+            assert abs(res[k] - v) <= 2e-3, (k, res[k], v)
+        else:
+            assert float(res[k]) == v, (k, res[k], v)
+
+
+def test_evaluate_model_scores_the_models_own_fusion_when_it_cannot_restate_it():
+    """A model whose ``outputs['segmentation']`` is NOT what its fusion attributes say (here: an extra bias) must be
+    scored on its own fused logits -- the reference scores outputs['segmentation'] (evaluate.py:178-179) -- with the
+    members feeding only the disagreement histogram; and a model without the fusion attributes likewise."""
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200.evaluation import evaluate_model
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import RobustnessMetrics
+    batches = _loader(21)
+    bias = torch.linspace(-1, 1, C).view(1, C, 1, 1)
+
+    class _Odd(_Ensemble):
+        def __init__(self, batches, with_attrs):
+            super().__init__(batches)
+            self.segformer = torch.nn.Identity()       # evaluate.py:196 keys the ensemble statistics on this attribute
+            if not with_attrs:
+                del self.ensemble_weights, self.temperature
+                del self.ensemble_strategy, self.temperature_scaling
+
+        def forward(self, x):
+            out = super().forward(x)
+            out["segmentation"] = (0.5 * out["segformer_seg"] + 0.5 * out["deeplabv3plus_seg"]) + bias.cuda()
+            return out
+
+    want = _expected(batches, lambda a, b: (0.5 * a + 0.5 * b) + bias)
+    for with_attrs in (True, False):
+        res = evaluate_model(_Odd(batches, with_attrs), batches, RobustnessMetrics(C), torch.device("cuda"),
+                             _Config({"data.weather_conditions": CONDS}))
+        _check(res, want)
+        tg = torch.cat([b["label"] for b in batches])
+        exact = om.disagreement_auroc([torch.cat([b["_la"] for b in batches]), torch.cat([b["_lb"] for b in batches])], tg)
+        assert abs(res["ensemble_disagreement_auroc"] - exact) <= 2e-3
 
 
 def test_evaluate_model_single_member():

@@ -175,6 +175,69 @@ def test_ensemble_training_gradients(pkg):
         _close(gg.cpu().numpy(), ww.numpy(), 2e-4, 1e-8)
 
 
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_temperature_only_gradient_with_frozen_members(pkg, mode):
+    """Post-hoc calibration: frozen (detached) members, frozen fusion weights, trainable temperature, in eval() mode
+    as well as train().  The reference's eager expression always carries autograd to `temperature`
+    (models/model.py:443-462); the drop-in must too, with the same value."""
+    from oracle import fusion as of_
+    torch.manual_seed(5)
+    b, c, h, w = 2, 19, 12, 20
+    a0, b0 = torch.randn(b, c, h, w), torch.randn(b, c, h, w)
+    lab = torch.randint(0, c, (b, h, w))
+    ens = pkg.EnsembleModel(c, False, "weighted_average", True, segformer=_Fixed(a0), deeplabv3plus=_Fixed(b0))
+    with torch.no_grad():
+        ens.ensemble_weights.copy_(torch.tensor([0.3, 0.9]))
+        ens.temperature.copy_(torch.tensor([1.7]))
+    ens.ensemble_weights.requires_grad_(False)
+    getattr(ens, mode)()
+    out = ens(torch.zeros(b, 3, h, w))["segmentation"]
+    assert out.requires_grad, "the fused logits must carry a graph to the temperature"
+    torch.nn.functional.cross_entropy(out, lab.to(out.device)).backward()
+    assert ens.ensemble_weights.grad is None
+    t = torch.tensor([1.7], requires_grad=True)
+    ref = of_.fuse_logits(a0, b0, "weighted_average", torch.tensor([0.3, 0.9]), t)
+    torch.nn.functional.cross_entropy(ref, lab).backward()
+    _close(ens.temperature.grad.cpu().numpy(), t.grad.numpy(), 2e-4, 1e-8)
+    # ConfidenceCalibration.temperature_scale is the reference's `logits / temperature`: differentiable as well
+    cal = pkg.ConfidenceCalibration()
+    t2 = torch.tensor([2.5], requires_grad=True)
+    x = a0.clone().requires_grad_(True)
+    y = cal.temperature_scale(x, t2)
+    assert torch.equal(y.detach().cpu(), a0 / torch.tensor([2.5]))
+    (y * y).sum().backward()
+    t3 = torch.tensor([2.5], requires_grad=True)
+    x3 = a0.clone().requires_grad_(True)
+    ((x3 / t3) ** 2).sum().backward()
+    _close(t2.grad.cpu().numpy(), t3.grad.numpy(), 2e-4, 1e-6)
+    _close(x.grad.cpu().numpy(), x3.grad.numpy(), 1e-5, 1e-8)
+    # without grad mode (or nothing trainable) the plain kernel path is taken
+    with torch.no_grad():
+        assert not ens(torch.zeros(b, 3, h, w))["segmentation"].requires_grad
+
+
+def test_ops_follow_the_device_of_their_operands(pkg):
+    """Tensors on cuda:1 while cuda:0 is current: the wrappers must switch device (outputs, bins and workspaces on
+    cuda:1, kernels launched there) instead of launching on device 0 with device-1 pointers."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from adverse_weather_semantic_segmentation_robustness_benchmark_b200 import ops, _lib
+    torch.cuda.set_device(0)
+    d1 = torch.device("cuda", 1)
+    gen = torch.Generator().manual_seed(2)
+    la, lb = torch.randn(1, 19, 16, 32, generator=gen), torch.randn(1, 19, 16, 32, generator=gen)
+    tgt = torch.randint(0, 19, (1, 16, 32), generator=gen)
+    kw = dict(strategy=_lib.FUSE_WEIGHTED, w0=0.4, w1=0.6, temperature=1.3, auroc_bins=1024)
+    want = ops.score(la, lb, tgt, **kw)["bins"].cpu()                      # on cuda:0
+    got = ops.score(la.to(d1), lb.to(d1), tgt, **kw)["bins"]              # members on cuda:1, labels on the host
+    assert got.device == d1 and torch.equal(got.cpu(), want)
+    assert torch.cuda.current_device() == 0
+    with pytest.raises(ValueError, match="different CUDA devices"):
+        ops.score(la.to(d1), lb.cuda(0), tgt, **kw)
+    out = pkg.FogDensityAwareLoss()({"segmentation": la.to(d1).requires_grad_(True)}, {"label": tgt.to(d1)})
+    assert out["total_loss"].device == d1
+
+
 def test_depth_density_forward_backward(pkg, golden):
     """_estimate_fog_density_from_depth in libawx: forward against the reference's golden output, gradient
     against autograd of the oracle's restatement (the indicator edge mask carries no gradient; min / max do)."""

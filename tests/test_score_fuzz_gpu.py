@@ -66,7 +66,8 @@ def test_score_fuzz(seed):
     err = (out["mi"].cpu() - mi_ref).abs() - (1e-5 * mi_ref.abs() + 2e-6)
     assert float(err.max()) <= 0, f"MI excess {float(err.max()):.2e}"
     wrong = (om.mean_prob_prediction([la, lb]) != tgt) & valid
-    parity.assert_ens_wrong_parity(bins, int(wrong.sum()), int(valid.sum()), _lib, floor=2)
+    # saturated softmaxes (logit scale 12) tie for real: the cap on the reported ties is their fp64 count
+    parity.assert_ens_wrong_parity(bins, int(wrong.sum()), int(valid.sum()), _lib, cap=parity.genuine_marg_ties([la, lb], tgt))
     # bins only
     fast = ops.read_bins(ops.score(la, lb, tgt, **kw)["bins"], C, 15, 4096)
     assert np.array_equal(fast.confusion, bins.confusion)

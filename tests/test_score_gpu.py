@@ -356,7 +356,7 @@ def test_full_size_properties(pkg):
     # differ only where the kernel reported a tie of the top probabilities
     assert abs(int(bins.ece_correct.sum()) - bins.counter(_lib.CNT_CORRECT)) <= bins.counter(_lib.CNT_EPRED_AMBIG)
     for k in (_lib.CNT_ECE_AMBIG, _lib.CNT_EPRED_AMBIG, _lib.CNT_MARG_AMBIG):
-        assert bins.counter(k) <= parity.amb_bound(n_valid), k
+        assert bins.counter(k) <= parity.amb_bound(n_valid, 5e-6), k
     # against torch on the device for the integer parts
     fused = (0.5 * la + 0.5 * lb) / torch.tensor([1.7], device=dev)  # tensor divisor: true division on CUDA
     assert torch.equal(out["pred"].long(), fused.argmax(1))
@@ -406,8 +406,10 @@ def test_full_size_bins_only_kernels_match_generic(pkg, mode, temp, ldt):
     n_valid = int((tgt_c != 255).sum())
     ref = om.ece(want, tgt_c)
     assert np.array_equal(fast.confusion, om.confusion_matrix(want, tgt_c, c).numpy())
+    cap = parity.genuine_ece_near_edges(want, tgt_c)
+    assert cap <= 1e-5 * n_valid      # the data itself: a few pixels per million sit on an edge
     for b_ in (fast, slow):
-        parity.assert_ece_parity(b_, ref, n_valid, _lib)
+        parity.assert_ece_parity(b_, ref, n_valid, _lib, cap=cap)
         if nb:
             wrong = int(((om.mean_prob_prediction([la_c, lb_c]) != tgt_c) & (tgt_c != 255)).sum())
             parity.assert_ens_wrong_parity(b_, wrong, n_valid, _lib)

@@ -30,3 +30,30 @@ class ReplayModel(torch.nn.Module):
         if "_depth" in b:
             out["depth"] = b["_depth"]
         return {k: v.to(self.device) for k, v in out.items()} if self.device is not None else out
+
+
+def evaluate_fixture_batches(g, tag):
+    """The test loader stored in tests/golden/evaluate.npz (make_golden.py::evaluate_cases): labels, weather
+    conditions and both members' logits per batch; the images are placeholders (the models replay stored logits)."""
+    nb, bsz = int(g[f"{tag}_args"][1]), int(g[f"{tag}_args"][2])
+    batches = []
+    for i in range(nb):
+        b = {"image": torch.zeros(bsz, 3, 4, 4)}
+        for k in ("label", "_la", "_lb"):
+            b[k] = torch.from_numpy(g[f"{tag}_b{i}_{k}"])
+        b["weather_condition"] = [str(x) for x in g[f"{tag}_b{i}_weather_condition"]]
+        batches.append(b)
+    return batches
+
+
+class ReplayMember(torch.nn.Module):
+    """One ensemble member replaying the stored logits of successive batches."""
+
+    def __init__(self, batches, key, device=None):
+        super().__init__()
+        self.batches, self.key, self.i, self.device = batches, key, 0, device
+
+    def forward(self, x):
+        out = self.batches[self.i][self.key]
+        self.i += 1
+        return {"segmentation": out.to(self.device) if self.device is not None else out}
