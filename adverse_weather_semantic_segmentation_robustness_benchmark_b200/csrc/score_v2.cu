@@ -18,11 +18,19 @@
 // piecewise-constant real data; ECE bins are private to the warp (32-bit packed words, flushed to
 // 64-bit before they can overflow).  Pixels with non-finite sums (NaN / inf logits) and pixels
 // within 16 ulp of an ECE edge take the scalar slow paths shared with kernel v1.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstring>
+
 #include "score_common.cuh"
 #include "tma_ring.cuh"
 
 #ifndef AWX_V2_GROUPS
 #define AWX_V2_GROUPS 3
+#endif
+#ifndef AWX_V2_TMAP
+#define AWX_V2_TMAP 0   // 2-D tensor-map copies: built and measured (1-2 % slower than the bulk copies), kept as a build option
 #endif
 
 namespace awx {
@@ -52,6 +60,14 @@ struct Geo {
     return g * (CW / kGroups) + (g < CW % kGroups ? g : CW % kGroups);
   }
   __host__ __device__ static constexpr int group_warps(int g) { return CW / kGroups + (g < CW % kGroups ? 1 : 0); }
+  // Build option AWX_V2_TMAP=1: equal groups of at most 256 pixels are fetched with ONE 2-D tensor-map copy per member
+  // and chunk (box = kBoxW pixels x 19 planes, SASS UTMALDG) instead of 19 bulk copies -- 2 * kGroups copy
+  // instructions per tile instead of 38 * kGroups, and (every completed copy wakes every warp sleeping on an mbarrier
+  // of the CTA) ~150 fewer SYNCS / NANOSLEEP / BRA per pixel.  Measured on B200 it is nevertheless 1-2 % SLOWER in
+  // the bench step than the bulk copies (profiles/r2h_ab_bench.md), so the default is off.  The box lands densely: a
+  // unit is then [group][member][plane][kBoxW] instead of [member][plane][kTP].
+  static constexpr bool kTensorMap = AWX_V2_TMAP != 0 && CW % kGroups == 0 && kTP / kGroups <= 256;
+  static constexpr int kBoxW = kTP / kGroups;
   __host__ __device__ static constexpr int group_of_warp(int w) {
     int g = 0;
     for (int i = 1; i < kGroups; ++i) g += (w >= group_first_warp(i)) ? 1 : 0;
@@ -202,13 +218,18 @@ __device__ __noinline__ void slow_pixel(const ScoreParams& p, const float* s_edg
 // Shared memory: [mbarriers | counters | confusion | edges | per-warp ECE words | AUROC | ring].
 template <int MODE, bool JS, int FAST, int DIV, int CW>
 __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
-    score_v2_kernel(const __grid_constant__ ScoreParams p, const int NU, const float negzero) {
+    score_v2_kernel(const __grid_constant__ ScoreParams p, const int NU, const float negzero,
+                    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b) {
   using G = Geo<CW>;
   constexpr int kTP = G::kTP, kCons = G::kCons, kConsWarps = CW, kV2Threads = G::kThreads;
   constexpr bool ENS = MODE != 0;
   // one ring unit = one tile of every member (19 or 38 planes): consumers wait once and release once per tile
   constexpr int kUnitFloats = (ENS ? 2 : 1) * G::kUnitFloats;
   constexpr uint32_t kUnitBytes = 4u * kUnitFloats;
+  constexpr bool TM = G::kTensorMap;
+  constexpr int kM = ENS ? 2 : 1;
+  constexpr int kPS = TM ? G::kBoxW : kTP;      // plane stride inside a unit (floats)
+  constexpr int kMO = kC * kPS;                 // offset of the second member's planes (floats)
   constexpr int NP = (kC + 1) / 2;  // 10 class pairs
   constexpr float kDummy = -1e30f;
   // bins-only kernels: 15 ECE bins and 4096 (ensemble) / 0 (single) AUROC bins are compile-time constants, so
@@ -280,14 +301,24 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
         // after the other (ELECT / 4 x R2UR / UBLKCP per copy: ~190 instructions per unit, which kept this warp
         // busy 70 % of the time)
         if (elect_one()) {
-          mbar_expect_tx(fb, (ENS ? 2u : 1u) * kC * (unsigned)n * 4u);
-          if (n > 0) {
-            float* dst = units + (size_t)u * kUnitFloats + c0;
+          if (TM) {
+            // out-of-image pixels of a tail tile are zero-filled by the copy engine and still count as bytes
+            mbar_expect_tx(fb, n > 0 ? (unsigned)(kM * kC * G::kBoxW * 4) : 0u);
+            if (n > 0) {
+              float* dst = units + (size_t)u * kUnitFloats + (size_t)g * (kM * kMO);
+              tma_load_2d(dst, &tmap_a, (int)(p0 + c0), (int)(img * kC), fb);
+              if (ENS) tma_load_2d(dst + kMO, &tmap_b, (int)(p0 + c0), (int)(img * kC), fb);
+            }
+          } else {
+            mbar_expect_tx(fb, (ENS ? 2u : 1u) * kC * (unsigned)n * 4u);
+            if (n > 0) {
+              float* dst = units + (size_t)u * kUnitFloats + c0;
 #pragma unroll
-            for (int m = 0; m < (ENS ? 2 : 1); ++m) {
-              const float* src = (m == 0 ? p.a : p.b) + img * kC * HW + p0 + c0;
+              for (int m = 0; m < (ENS ? 2 : 1); ++m) {
+                const float* src = (m == 0 ? p.a : p.b) + img * kC * HW + p0 + c0;
 #pragma unroll
-              for (int c = 0; c < kC; ++c) bulk_load(dst + (m * kC + c) * kTP, src + c * HW, (unsigned)n * 4u, fb);
+                for (int c = 0; c < kC; ++c) bulk_load(dst + (m * kC + c) * kTP, src + c * HW, (unsigned)n * 4u, fb);
+              }
             }
           }
         }
@@ -324,7 +355,9 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   // this warp's group: full[u][grp] at my_bar0 + 8 kMaxGroups u, empty[u][grp] kMaxUnits * kMaxGroups words further
   const uint32_t sbase = smem_u32(smem);
   const uint32_t my_bar0 = sbase + 8u * (uint32_t)G::group_of_warp(warp);
-  const uint32_t my_unit0 = sbase + (uint32_t)v2_ring_offset(kConsWarps, nb, NB) + 4u * (uint32_t)t;
+  const int grp = G::group_of_warp(warp);
+  const uint32_t my_unit0 = sbase + (uint32_t)v2_ring_offset(kConsWarps, nb, NB) +
+                            4u * (uint32_t)(TM ? grp * (kM * kMO) + (t - 32 * G::group_first_warp(grp)) : t);
   // B * HW < 2^32 (score_v2_supported): all pixel and tile indices of the consumers are 32 bit
   const unsigned HWu = (unsigned)HW, tpiu = (unsigned)tpi, ntu = (unsigned)ntiles;
   unsigned img = blockIdx.x / tpiu, tin = blockIdx.x - img * tpiu;
@@ -353,14 +386,14 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       const uint32_t s = my_unit0 + u * kUnitBytes;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        a[i].x = lds_f32(s + (2 * i) * kTP * 4);
-        a[i].y = (2 * i + 1 < kC) ? lds_f32(s + (2 * i + 1) * kTP * 4) : kDummy;
+        a[i].x = lds_f32(s + (2 * i) * kPS * 4);
+        a[i].y = (2 * i + 1 < kC) ? lds_f32(s + (2 * i + 1) * kPS * 4) : kDummy;
       }
       if (ENS) {
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          b[ENS ? i : 0].x = lds_f32(s + (kC + 2 * i) * kTP * 4);
-          b[ENS ? i : 0].y = (2 * i + 1 < kC) ? lds_f32(s + (kC + 2 * i + 1) * kTP * 4) : kDummy;
+          b[ENS ? i : 0].x = lds_f32(s + (kMO + (2 * i) * kPS) * 4);
+          b[ENS ? i : 0].y = (2 * i + 1 < kC) ? lds_f32(s + (kMO + (2 * i + 1) * kPS) * 4) : kDummy;
         }
       }
       // max-confidence kernels keep the unit until the winning member's logits have been re-read (see P0)
@@ -493,22 +526,22 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
       n_pick += act && fabsf(ca - cb) <= 4.8e-7f * fmaxf(ca, cb);
       w0s = pick_a ? 1.f : 0.f;
       w1s = pick_a ? 0.f : 1.f;
-      const uint32_t sv = held_unit + (pick_a ? 0u : (uint32_t)(kC * kTP * 4));
+      const uint32_t sv = held_unit + (pick_a ? 0u : (uint32_t)(kMO * 4));
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        v[i].x = lds_f32(sv + (2 * i) * kTP * 4);
-        v[i].y = (2 * i + 1 < kC) ? lds_f32(sv + (2 * i + 1) * kTP * 4) : kDummy;
+        v[i].x = lds_f32(sv + (2 * i) * kPS * 4);
+        v[i].y = (2 * i + 1 < kC) ? lds_f32(sv + (2 * i + 1) * kPS * 4) : kDummy;
       }
       if (FAST == 0 && p.fused != nullptr) {
         // the fused-logit MAP is the reference's expression as written, mask*l1 + (1-mask)*l2: the other member
         // enters as 0 * x (a signed zero, or NaN for an infinite logit)
-        const uint32_t so = held_unit + (pick_a ? (uint32_t)(kC * kTP * 4) : 0u);
+        const uint32_t so = held_unit + (pick_a ? (uint32_t)(kMO * 4) : 0u);
         const float2 zero = splat(0.f);
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           float2 other;
-          other.x = lds_f32(so + (2 * i) * kTP * 4);
-          other.y = (2 * i + 1 < kC) ? lds_f32(so + (2 * i + 1) * kTP * 4) : 0.f;
+          other.x = lds_f32(so + (2 * i) * kPS * 4);
+          other.y = (2 * i + 1 < kC) ? lds_f32(so + (2 * i + 1) * kPS * 4) : 0.f;
           v[i] = add2(v[i], fma2(zero, other, nz));
         }
       }
@@ -834,6 +867,39 @@ __global__ void __launch_bounds__(Geo<CW>::kThreads, 1)
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  }();
+  return fn;
+}
+
+// logits [B, 19, HW] seen as a 2-D tensor [B * 19 planes][HW pixels]; box = box_w pixels x 19 planes
+int make_plane_map(CUtensorMap* tm, const float* base, long long planes, long long HW, int box_w) {
+  auto enc = tensor_map_encoder();
+  AWX_REQUIRE(enc != nullptr, AWX_E_UNSUPPORTED, "awx_score v2: cuTensorMapEncodeTiled is not available in this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)HW, (cuuint64_t)planes};
+  const cuuint64_t gstride[1] = {(cuuint64_t)HW * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)kC};
+  const cuuint32_t estr[2] = {1, 1};
+  static const CUtensorMapL2promotion promo = [] {   // dev knob AWX_V2_L2PROMO=0|1|2|3: none / 64 / 128 / 256 bytes
+    const char* e = getenv("AWX_V2_L2PROMO");
+    const int v = e ? atoi(e) : 0;
+    return v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+         : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  }();
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AWX_REQUIRE(r == CUDA_SUCCESS, AWX_E_UNSUPPORTED, "awx_score v2: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return AWX_OK;
+}
+
 template <int MODE, bool JS, int FAST, int DIV, int CW>
 int launch_v2(const ScoreParams& p, cudaStream_t stream) {
   using G = Geo<CW>;
@@ -855,7 +921,18 @@ int launch_v2(const ScoreParams& p, cudaStream_t stream) {
   const long long ntiles = p.B * ((p.HW + G::kTP - 1) / G::kTP);
   long long blocks = sm_count();
   if (blocks > ntiles) blocks = ntiles;
-  kern<<<(unsigned)blocks, G::kThreads, smem, stream>>>(p, nu, -0.0f);
+  CUtensorMap tma, tmb;
+  memset(&tma, 0, sizeof(tma));
+  memset(&tmb, 0, sizeof(tmb));
+  if (G::kTensorMap) {
+    int rc = make_plane_map(&tma, p.a, p.B * kC, p.HW, G::kBoxW);
+    if (rc != AWX_OK) return rc;
+    if (MODE != 0) {
+      rc = make_plane_map(&tmb, p.b, p.B * kC, p.HW, G::kBoxW);
+      if (rc != AWX_OK) return rc;
+    }
+  }
+  kern<<<(unsigned)blocks, G::kThreads, smem, stream>>>(p, nu, -0.0f, tma, tmb);
   AWX_CUDA(cudaGetLastError());
   note_launch();
   return AWX_OK;

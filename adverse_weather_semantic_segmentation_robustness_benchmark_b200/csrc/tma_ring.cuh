@@ -79,5 +79,16 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, unsig
                : "memory");
 }
 
+// 2-D tensor-map copy (cp.async.bulk.tensor, SASS UTMALDG): box (x .. x+w, y .. y+h) of the tensor described by
+// `tmap` (a __grid_constant__ CUtensorMap kernel parameter) into dense shared memory; elements outside the tensor
+// are zero-filled and the mbarrier is credited with the full box size either way
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int x, int y, u64* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
 }  // namespace
 }  // namespace awx

@@ -407,6 +407,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         cpu = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": cpu_kind(),
                "sample": cpu_sample_text(2, args.height, args.width) + f", {dt:.1f} s"}
 
+    # parity gates of the timed steps' own bins, before the side measurements reuse the evaluator
+    parity = parity_object(wl, results, world) if rank == 0 else None
     configs = None
     if not args.no_configs:
         configs = configs_object(wl, args, rank, world, barrier, max_over_ranks)
@@ -435,7 +437,7 @@ def run_gpu_arm(args, rank, world, local_rank):
                          "ms_per_launch": score_ms,
                          "whole_step_GBps": step_bytes / (ms_step * 1e-3) / 1e9},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "parity": parity_object(wl, results, world),
+            "parity": parity,
             "configs": configs,
         }
         line["parity"]["sharded_bins_equal_single"] = shard_ok

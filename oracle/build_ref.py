@@ -7,7 +7,7 @@ byte-compilation: the three files of SURVEY.md section 8a
     src/<pkg>/models/model.py            EnsembleModel, FogDensityAwareLoss      (8a rows 8-10)
     src/<pkg>/evaluation/metrics.py      IoU / ECE / disagreement / Robustness   (8a rows 11-14)
 
-are compiled from ``/root/reference`` straight into ``oracle/_ref/*.pyc`` -- build products only: no reference
+are compiled from ``/root/reference`` straight into ``oracle/_ref/*.refbin`` (marshalled code objects, the .pyc format) -- build products only: no reference
 source is copied into the repo, ``oracle/_ref/`` is git-ignored, and (like the repo's own ``libawx.so``) it travels to
 the GPU box with the snapshot, where ``/root/reference`` does not exist.  ``oracle/reference.py`` loads them.
 
@@ -25,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 REF_ROOT = os.environ.get("AWX_REFERENCE_ROOT", "/root/reference")
 PKG = "adverse_weather_semantic_segmentation_robustness_benchmark"
+EXT = ".refbin"   # .pyc content; the neutral extension keeps file-sync tools from dropping it as a cache file
 FILES = {"preprocessing": "data/preprocessing.py", "model": "models/model.py", "metrics": "evaluation/metrics.py"}
 
 
@@ -40,7 +41,7 @@ def build() -> str:
     meta = {"python": sys.version.split()[0], "magic": __import__("importlib.util").util.MAGIC_NUMBER.hex(), "files": {}}
     for name, rel in FILES.items():
         src = os.path.join(REF_ROOT, "src", PKG, rel)
-        py_compile.compile(src, cfile=os.path.join(OUT, name + ".pyc"), dfile=f"<reference>/{rel}", doraise=True,
+        py_compile.compile(src, cfile=os.path.join(OUT, name + EXT), dfile=f"<reference>/{rel}", doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
         meta["files"][name] = rel
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:

@@ -21,6 +21,7 @@ import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+EXT = ".refbin"
 _cache: dict = {}
 
 
@@ -33,7 +34,7 @@ def available() -> bool:
         return False
     if meta.get("magic") != importlib.util.MAGIC_NUMBER.hex():
         return False
-    return all(os.path.exists(os.path.join(REF_DIR, n + ".pyc")) for n in ("preprocessing", "model", "metrics"))
+    return all(os.path.exists(os.path.join(REF_DIR, n + EXT)) for n in ("preprocessing", "model", "metrics"))
 
 
 def module(name: str):
@@ -43,7 +44,7 @@ def module(name: str):
             # not installed in this image; only needed by the backbones, which the benchmark replaces by injected
             # logit producers
             sys.modules["segmentation_models_pytorch"] = types.ModuleType("segmentation_models_pytorch")
-        path = os.path.join(REF_DIR, name + ".pyc")
+        path = os.path.join(REF_DIR, name + EXT)
         loader = importlib.machinery.SourcelessFileLoader("_awx_ref_" + name, path)
         spec = importlib.util.spec_from_loader("_awx_ref_" + name, loader)
         mod = importlib.util.module_from_spec(spec)
