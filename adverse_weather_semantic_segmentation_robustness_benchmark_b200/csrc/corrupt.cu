@@ -15,9 +15,13 @@
 //   final: clip to [0,1], times 255, truncate toward zero
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "awx_internal.cuh"
 #include "raster.cuh"
 #include "convert.cuh"
+#include "blur_strip.cuh"
+#include "fog_fast.cuh"
 
 namespace awx {
 namespace {
@@ -96,14 +100,15 @@ __global__ void __launch_bounds__(128) rasterize_kernel(const AwxCorruptParams* 
 
 // ------------------------------------------------------------------- clean / fog / night
 template <typename FT>
-__global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t* __restrict__ img,
+__global__ void __launch_bounds__(kPointThreads, 5) pointwise_kernel(const uint8_t* __restrict__ img,
                                                                    uint8_t* __restrict__ out,
                                                                    const AwxCorruptParams* __restrict__ params,
                                                                    const FT* __restrict__ field, long long HW,
-                                                                   const __grid_constant__ NormOut norm) {
+                                                                   const __grid_constant__ NormOut norm, int fog_elsewhere) {
   const int b = blockIdx.y;
   const AwxCorruptParams prm = params[b];
   if (prm.kind != AWX_CLEAN && prm.kind != AWX_FOG && prm.kind != AWX_NIGHT) return;
+  if (prm.kind == AWX_FOG && fog_elsewhere && prm.field_offset % 2 == 0 && fog::params_ok(prm.d0, prm.d1)) return;  // fog_kernel has this image
   __shared__ __align__(16) unsigned s_in[kChunkPx * 3 / 4];
   __shared__ __align__(16) unsigned s_out[kChunkPx * 3 / 4];
   const uint8_t* src = img + (size_t)b * HW * 3;
@@ -203,6 +208,55 @@ __global__ void __launch_bounds__(kPointThreads) pointwise_kernel(const uint8_t*
       for (int i = threadIdx.x; i < npx * 3; i += kPointThreads) dst[px0 * 3 + i] = sb[i];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------ fog, screened
+// fog_fast.cuh: an fp32 screen decides the byte wherever 255 v is not within 3e-4 of an integer, the reference's fp64
+// expression (exp and all) runs for the ~2e-3 of the pixels it cannot decide; outputs are those of
+// pointwise_kernel<double> bit for bit (tests/test_fog_fast_cpu.py, tests/test_fog_fast_gpu.py).
+// No shared memory, no barrier: a thread owns a UNIT of 16 pixels -- 48 bytes in (3 x 16 B), 16 fp64 depths (8 x 16 B),
+// 48 bytes out -- all eleven loads are issued before the first use, and consecutive lanes touch consecutive units, so
+// every warp-wide access is contiguous.  Needs H*W % 16 == 0 and 16-byte aligned tensors; anything else goes to the
+// generic kernel.
+constexpr int kFogThreads = 256;
+__global__ void __launch_bounds__(kFogThreads, 3) fog_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
+                                                              const AwxCorruptParams* __restrict__ params,
+                                                              const double* __restrict__ field, long long HW) {
+  const int b = blockIdx.y;
+  const AwxCorruptParams prm = params[b];
+  if (prm.kind != AWX_FOG || prm.field_offset % 2 != 0 || !fog::params_ok(prm.d0, prm.d1)) return;  // the generic kernel has it
+  const uint4* src = reinterpret_cast<const uint4*>(img + (size_t)b * HW * 3);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * HW * 3);
+  const double2* fld = reinterpret_cast<const double2*>(field + prm.field_offset);
+  const fog::Params fp = fog::make_params(prm.d0, prm.d1);
+  const long long units = HW / 16;
+  for (long long u = (long long)blockIdx.x * kFogThreads + threadIdx.x; u < units; u += (long long)gridDim.x * kFogThreads) {
+    double2 d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = __ldg(fld + u * 8 + i);
+    uint4 w[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = ld_stream_u4(src + u * 3 + i);
+    const unsigned wi[12] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w, w[2].x, w[2].y, w[2].z, w[2].w};
+    unsigned wo[12];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {  // four pixels = three words at a time
+      const unsigned in3[3] = {wi[3 * g], wi[3 * g + 1], wi[3 * g + 2]};
+      const double dep[4] = {d[2 * g].x, d[2 * g].y, d[2 * g + 1].x, d[2 * g + 1].y};
+      unsigned o3[3];
+      fog::fog4(in3, dep, fp, o3);
+      wo[3 * g] = o3[0];
+      wo[3 * g + 1] = o3[1];
+      wo[3 * g + 2] = o3[2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) st_stream_u4(dst + u * 3 + i, make_uint4(wo[4 * i], wo[4 * i + 1], wo[4 * i + 2], wo[4 * i + 3]));
+  }
+}
+
+// the screened fog kernel takes whole 16-pixel units of 16-byte aligned tensors
+bool fog_kernel_ok(const uint8_t* img, const uint8_t* out, const void* field, long long HW) {
+  return HW % 16 == 0 && (((uintptr_t)img | (uintptr_t)out | (uintptr_t)field) & 15) == 0;
 }
 
 // --------------------------------------------------------------------------- rain / snow
@@ -344,16 +398,17 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
       const float* p = w + LEAD + 3 * R + e;  // centre tap
       float v;
       if (R == 1) {
-        v = p[0] * t0 + (p[-3] + p[3]) * t1;
+        v = fmaf(p[0], t0, __fmul_rn(p[-3] + p[3], t1));  // SymmRowSmallVec_32f: the side product is rounded, the centre fused
       } else {
-        // generic row filter order: leftmost tap first
-        v = p[-9] * t3;
-        v += p[-6] * t2;
-        v += p[-3] * t1;
-        v += p[0] * t0;
-        v += p[3] * t1;
-        v += p[6] * t2;
-        v += p[9] * t3;
+        // RowVec_32f: leftmost tap first, its product rounded, every further tap fused (written out: left to the
+        // compiler, `a * b + c * d` fuses the FIRST product and rounds the second)
+        v = __fmul_rn(p[-9], t3);
+        v = fmaf(p[-6], t2, v);
+        v = fmaf(p[-3], t1, v);
+        v = fmaf(p[0], t0, v);
+        v = fmaf(p[3], t1, v);
+        v = fmaf(p[6], t2, v);
+        v = fmaf(p[9], t3, v);
       }
       r[e] = v;
     }
@@ -382,10 +437,10 @@ __global__ void __launch_bounds__(kBlurThreads) blur_kernel(const uint8_t* __res
       const int ry = half * VR + rr;
       if (ry >= th) break;
       auto vfilt = [&](float c0, float m1, float p1, float m2, float p2, float m3, float p3) -> unsigned {
-        float v = c0 * t0 + (m1 + p1) * t1;
+        float v = fmaf(m1 + p1, t1, __fmul_rn(c0, t0));  // SymmColumnVec_32f: the centre product is rounded, the rest fused
         if (R == 3) {
-          v += (m2 + p2) * t2;
-          v += (m3 + p3) * t3;
+          v = fmaf(m2 + p2, t2, v);
+          v = fmaf(m3 + p3, t3, v);
         }
         return to_u8_f32(v);
       };
@@ -464,6 +519,153 @@ int launch_blur(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparam
   return AWX_OK;
 }
 
+// ------------------------------------------------------------- rain / snow, row-walking strip kernel
+// blur_strip.cuh has the design and the per-thread code (shared with the host emulation of the tests).  This is the
+// CTA: strip = blockIdx.x (32 units = 512 pixels), row segment = blockIdx.y, image = blockIdx.z.  One barrier per
+// iteration (the filtered rows are double buffered); the global loads of the NEXT iteration's row are issued before
+// the barrier, so they are in flight while the V phase runs.
+template <int R, bool RAIN>
+__global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
+    blur_strip_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, const AwxCorruptParams* __restrict__ params,
+                      const unsigned* __restrict__ mask, int H, int W, int WW, int seg, float negzero) {
+  using G = strip::Geo<R>;
+  constexpr int NR = G::kNR;
+  const int b = blockIdx.z;
+  const AwxCorruptParams prm = params[b];
+  if (prm.kind != (RAIN ? AWX_RAIN : AWX_SNOW) || prm.blur_k != 2 * R + 1) return;
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  float4* s_h = reinterpret_cast<float4*>(smem);  // [2][NR][G::kRowFloat4]
+
+  const int NU = W / strip::kUnitPx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * strip::kStripUnits + lane;
+  const bool hact = unit < NU;
+  const int ys = blockIdx.y * seg, ye = min(ys + seg, H);
+  const int nH = ye - ys + 2 * R;  // filtered rows this CTA produces: ys - R .. ye + R - 1 (reflected)
+  const size_t row_bytes = (size_t)W * 3;
+  const uint8_t* src = img + (size_t)b * H * row_bytes;
+  uint8_t* dst = out + (size_t)b * H * row_bytes;
+  const unsigned* m = mask + (size_t)b * H * WW;
+
+  strip::PointParams pp;
+  pp.k1 = prm.f0;
+  pp.k2 = prm.f1;
+  pp.t[0] = prm.taps[0];
+  pp.t[1] = prm.taps[1];
+  pp.t[2] = prm.taps[2];
+  pp.t[3] = prm.taps[3];
+  pp.negzero = negzero;
+
+  auto load_raw = [&](int hr, strip::Raw& r) {
+    const int sy = strip::reflect101(ys - R + hr, H);
+    const uint8_t* g = src + (size_t)sy * row_bytes + (size_t)unit * strip::kUnitE;
+    const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(g)), c1 = __ldg(reinterpret_cast<const uint4*>(g + 16)),
+                c2 = __ldg(reinterpret_cast<const uint4*>(g + 32));
+    uint4 l = make_uint4(0, 0, 0, 0), rr = make_uint4(0, 0, 0, 0);
+    if (unit > 0) l = __ldg(reinterpret_cast<const uint4*>(g - 16));
+    if (unit + 1 < NU) rr = __ldg(reinterpret_cast<const uint4*>(g + 48));
+    r.own[0] = c0.x, r.own[1] = c0.y, r.own[2] = c0.z, r.own[3] = c0.w;
+    r.own[4] = c1.x, r.own[5] = c1.y, r.own[6] = c1.z, r.own[7] = c1.w;
+    r.own[8] = c2.x, r.own[9] = c2.y, r.own[10] = c2.z, r.own[11] = c2.w;
+    r.hl[0] = l.y, r.hl[1] = l.z, r.hl[2] = l.w;
+    r.hr[0] = rr.x, r.hr[1] = rr.y, r.hr[2] = rr.z;
+    strip::mask_words(m + (size_t)sy * WW, unit, WW, r.m0, r.m1);
+  };
+
+  // V-phase ownership
+  const int g = threadIdx.x;
+  const int vu = g / 6, vkg = g - vu * 6;
+  const int vunit = blockIdx.x * strip::kStripUnits + vu;
+  const bool vact = g < strip::kGroups && vunit < NU;
+  const int vslot0 = strip::group_slot(g < strip::kGroups ? g : 0, 0), vslot1 = strip::group_slot(g < strip::kGroups ? g : 0, 1);
+  // the thread's output pointer walks down the rows: row ys - 2R (virtual) at the first filtered row
+  uint8_t* vdst = dst + (size_t)vunit * strip::kUnitE + vkg * 4 + ((ptrdiff_t)ys - 2 * R) * (ptrdiff_t)row_bytes;
+
+  strip::Raw raw;
+  if (hact && warp < nH) load_raw(warp, raw);
+  strip::Window<R> win;
+  constexpr unsigned kOvBits = ((1u << (strip::kUnitPx + 2 * R)) - 1u) << (8 - R);  // the pixels the filter can reach
+
+  const int iters = (nH + NR - 1) / NR;
+  int buf = 0;
+  for (int it = 0; it < iters; ++it) {
+    const int hr = it * NR + warp;
+    const bool hrow = hact && hr < nH;
+    float4* rowbuf = s_h + (size_t)(buf * NR + warp) * G::kRowFloat4;
+    auto store = [&](int q, const strip::F2& a, const strip::F2& c) {
+      rowbuf[strip::quad_slot(lane, q)] = make_float4(a.x, a.y, c.x, c.y);
+    };
+    // overlays are rare per pixel but not per warp: one vote picks the instruction stream with or without selects
+    if (hrow) strip::finish_raw(raw, unit, NU);
+    const bool any_ov = __any_sync(0xffffffffu, hrow && (raw.mb & kOvBits) != 0u);
+    if (hrow) {
+      if (any_ov)
+        strip::h_row<R, RAIN, true>(raw, pp, store);
+      else
+        strip::h_row<R, RAIN, false>(raw, pp, store);
+    }
+    if (hact && hr + NR < nH) load_raw(hr + NR, raw);
+    __syncthreads();
+    if (vact) {
+      const float4* vb = s_h + (size_t)(buf * NR) * G::kRowFloat4;
+#define AWX_VROW(J)                                                                                          \
+  if constexpr ((J) < NR) {                                                                                  \
+    const int hj = it * NR + (J);                                                                            \
+    if (hj < nH) {                                                                                           \
+      const float4 a = vb[(J) * G::kRowFloat4 + vslot0], c = vb[(J) * G::kRowFloat4 + vslot1];               \
+      unsigned wlo, whi;                                                                                     \
+      const bool emit = hj >= 2 * R;                                                                         \
+      strip::v_row<R, (J)>(win, strip::Quad{a.x, a.y, a.z, a.w}, strip::Quad{c.x, c.y, c.z, c.w}, pp.t, emit, wlo, whi); \
+      if (emit) {                                                                                            \
+        *reinterpret_cast<unsigned*>(vdst) = wlo;                                                            \
+        *reinterpret_cast<unsigned*>(vdst + 24) = whi;                                                       \
+      }                                                                                                      \
+      vdst += row_bytes;                                                                                     \
+    }                                                                                                        \
+  }
+      AWX_VROW(0) AWX_VROW(1) AWX_VROW(2) AWX_VROW(3) AWX_VROW(4) AWX_VROW(5) AWX_VROW(6)
+#undef AWX_VROW
+    }
+    buf ^= 1;
+  }
+}
+
+template <int R, bool RAIN>
+int launch_blur_strip(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparams, const unsigned* mask, int64_t B,
+                      int64_t n_match, int H, int W, int WW, cudaStream_t s) {
+  using G = strip::Geo<R>;
+  auto kern = blur_strip_kernel<R, RAIN>;
+  AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+  const int strips = (W / strip::kUnitPx + strip::kStripUnits - 1) / strip::kStripUnits;
+  // Row segments: a CTA filters seg + 2R rows to emit seg, and the launch runs in waves of 2 CTAs per SM; pick the
+  // segment count that minimises waves x rows per CTA (long segments amortise the vertical halo, short ones fill the
+  // last wave), between 32 and 128 rows per segment.
+  const long long slots = 2LL * sm_count();
+  const long long lo = (H + 127) / 128, hi = H / 32 > 0 ? H / 32 : 1;
+  long long best = lo, best_cost = -1;
+  for (long long n = lo; n <= hi; ++n) {
+    const long long sg = (H + n - 1) / n, ctas = (long long)strips * ((H + sg - 1) / sg) * n_match;
+    const long long cost = ((ctas + slots - 1) / slots) * (sg + 2 * R + 4);
+    if (best_cost < 0 || cost < best_cost) best = n, best_cost = cost;
+  }
+  const int seg = (int)((H + best - 1) / best);
+  dim3 grid((unsigned)strips, (unsigned)((H + seg - 1) / seg), (unsigned)B);
+  kern<<<grid, G::kThreads, G::kSmemBytes, s>>>(img, out, dparams, mask, H, W, WW, seg, -0.0f);
+  AWX_CUDA(cudaGetLastError());
+  note_launch();
+  return AWX_OK;
+}
+
+// the strip kernel needs whole 16-pixel units, 16-byte aligned rows and a uint8 output; AWX_BLUR_KERNEL=tile forces the
+// tile kernel (A/B measurements, parity tests of both)
+bool strip_kernel_ok(const uint8_t* img, const uint8_t* out, const NormOut& norm, int H, int W) {
+  const char* e = getenv("AWX_BLUR_KERNEL");  // read per call: the parity tests switch kernels within one process
+  const bool forced_tile = e && e[0] == 't';
+  return !forced_tile && out != nullptr && norm.ptr == nullptr && W % strip::kUnitPx == 0 && H >= 1 &&
+         (((uintptr_t)img | (uintptr_t)out) & 15) == 0;
+}
+
 size_t params_bytes(int64_t B) { return ((size_t)B * sizeof(AwxCorruptParams) + 255) & ~(size_t)255; }
 
 // ------------------------------------------------------------------------ synthetic depth
@@ -529,14 +731,24 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
   AWX_REQUIRE(img && (out || norm.ptr) && params && workspace, AWX_E_ARG, "awx_corrupt: NULL pointer (img/out/params/workspace)");
   AWX_REQUIRE(batch <= 65535, AWX_E_UNSUPPORTED, "awx_corrupt: batch %lld > 65535 per call", (long long)batch);
   AWX_REQUIRE(field_dtype == AWX_F32 || field_dtype == AWX_F64, AWX_E_ARG, "awx_corrupt: unknown field dtype %d", field_dtype);
-  bool any_point = false, any_overlay = false, blur[4] = {false, false, false, false};  // rain 3 / 7, snow 3 / 7
+  // fog with fp64 depths and in-range coefficients goes to the screened kernel (AWX_FOG_KERNEL=exact: the generic
+  // pointwise kernel evaluates the fp64 expression for every pixel -- A/B measurements, parity tests of both)
+  const char* fog_env = getenv("AWX_FOG_KERNEL");
+  const bool fog_fast = !(fog_env && fog_env[0] == 'e') && field_dtype == AWX_F64 && out != nullptr && norm.ptr == nullptr &&
+                        fog_kernel_ok(img, out, field, (long long)H * W);
+  bool any_fog_fast = false;
+  bool any_point = false, any_overlay = false;
+  int64_t blur[4] = {0, 0, 0, 0};  // images per (kind, blur size): rain 3 / 7, snow 3 / 7
   for (int64_t b = 0; b < batch; ++b) {
     const AwxCorruptParams& q = params[b];
     switch (q.kind) {
       case AWX_CLEAN: any_point = true; break;
       case AWX_FOG:
       case AWX_NIGHT:
-        any_point = true;
+        if (q.kind == AWX_FOG && fog_fast && q.field_offset % 2 == 0 && fog::params_ok(q.d0, q.d1))
+          any_fog_fast = true;
+        else
+          any_point = true;
         AWX_REQUIRE(field != nullptr, AWX_E_ARG, "awx_corrupt: image %lld (fog/night) needs a depth/noise field", (long long)b);
         AWX_REQUIRE(q.field_offset >= 0, AWX_E_ARG, "awx_corrupt: negative field offset");
         break;
@@ -547,7 +759,7 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
         AWX_REQUIRE(q.item_count >= 0 && q.item_begin >= 0 && (int64_t)q.item_begin + q.item_count <= n_items, AWX_E_ARG,
                     "awx_corrupt: image %lld item range [%d,+%d) outside %lld items", (long long)b, q.item_begin, q.item_count, (long long)n_items);
         AWX_REQUIRE(q.item_count == 0 || items != nullptr, AWX_E_ARG, "awx_corrupt: items is NULL");
-        blur[(q.kind == AWX_RAIN ? 0 : 2) + (q.blur_k == 3 ? 0 : 1)] = true;
+        ++blur[(q.kind == AWX_RAIN ? 0 : 2) + (q.blur_k == 3 ? 0 : 1)];
         break;
       default:
         set_error("awx_corrupt: unknown kind %d for image %lld", q.kind, (long long)b);
@@ -563,11 +775,19 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
     const long long cap = (long long)sm_count() * 16;
     dim3 grid((unsigned)(chunks < cap ? chunks : cap), (unsigned)batch);
     if (field_dtype == AWX_F64)
-      pointwise_kernel<double><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW, norm);
+      pointwise_kernel<double><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW, norm, fog_fast ? 1 : 0);
     else
-      pointwise_kernel<float><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const float*>(field), HW, norm);
+      pointwise_kernel<float><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const float*>(field), HW, norm, 0);
     AWX_CUDA(cudaGetLastError());
-  note_launch();
+    note_launch();
+  }
+  if (any_fog_fast) {
+    long long blocks = (HW / 16 + kFogThreads - 1) / kFogThreads;
+    const long long cap = (long long)sm_count() * 12;
+    dim3 grid((unsigned)(blocks < cap ? blocks : cap), (unsigned)batch);
+    fog_kernel<<<grid, kFogThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW);
+    AWX_CUDA(cudaGetLastError());
+    note_launch();
   }
   if (any_overlay) {
     const int WW = (W + 31) / 32;
@@ -578,10 +798,17 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
   note_launch();
     int rc = AWX_OK;
     // one launch per (kind, blur size) present in the batch; every CTA of a launch skips the images of the others
-    if (blur[0]) rc = launch_blur<1, true>(img, out, dparams, mask, batch, H, W, WW, norm, s);
-    if (rc == AWX_OK && blur[1]) rc = launch_blur<3, true>(img, out, dparams, mask, batch, H, W, WW, norm, s);
-    if (rc == AWX_OK && blur[2]) rc = launch_blur<1, false>(img, out, dparams, mask, batch, H, W, WW, norm, s);
-    if (rc == AWX_OK && blur[3]) rc = launch_blur<3, false>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+    if (strip_kernel_ok(img, out, norm, H, W)) {
+      if (blur[0]) rc = launch_blur_strip<1, true>(img, out, dparams, mask, batch, blur[0], H, W, WW, s);
+      if (rc == AWX_OK && blur[1]) rc = launch_blur_strip<3, true>(img, out, dparams, mask, batch, blur[1], H, W, WW, s);
+      if (rc == AWX_OK && blur[2]) rc = launch_blur_strip<1, false>(img, out, dparams, mask, batch, blur[2], H, W, WW, s);
+      if (rc == AWX_OK && blur[3]) rc = launch_blur_strip<3, false>(img, out, dparams, mask, batch, blur[3], H, W, WW, s);
+    } else {
+      if (blur[0]) rc = launch_blur<1, true>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+      if (rc == AWX_OK && blur[1]) rc = launch_blur<3, true>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+      if (rc == AWX_OK && blur[2]) rc = launch_blur<1, false>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+      if (rc == AWX_OK && blur[3]) rc = launch_blur<3, false>(img, out, dparams, mask, batch, H, W, WW, norm, s);
+    }
     if (rc != AWX_OK) return rc;
   }
   return AWX_OK;
