@@ -46,7 +46,12 @@ struct Geo {
   static constexpr int kNR = R == 1 ? 6 : 7;          // rows per iteration = H-phase warps; a multiple of kD
   static constexpr int kThreads = kNR * 32;
   static constexpr int kRowFloat4 = 2 * kRowSlots;    // one filtered row in shared memory: [half][slot]
-  static constexpr int kSmemBytes = 2 * kNR * kRowFloat4 * 16;   // double buffered
+  // R = 3: the filtered rows are double buffered, one barrier per iteration, 2 CTAs per SM (the register window needs
+  // 128 registers per thread anyway).  R = 1 gets by with 80 registers: a single buffer and a second barrier per
+  // iteration let 4 CTAs (24 warps) share an SM, which hides both barriers and the dependent-issue latencies.
+  static constexpr int kBuffers = R == 1 ? 1 : 2;
+  static constexpr int kCtasPerSm = R == 1 ? 4 : 2;
+  static constexpr int kSmemBytes = kBuffers * kNR * kRowFloat4 * 16;
   static_assert(kNR % kD == 0, "static ring index");
   static_assert(kThreads >= kGroups, "every V group has a thread");
 };

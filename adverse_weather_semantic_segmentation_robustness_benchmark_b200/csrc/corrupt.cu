@@ -522,10 +522,23 @@ int launch_blur(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparam
 // ------------------------------------------------------------- rain / snow, row-walking strip kernel
 // blur_strip.cuh has the design and the per-thread code (shared with the host emulation of the tests).  This is the
 // CTA: strip = blockIdx.x (32 units = 512 pixels), row segment = blockIdx.y, image = blockIdx.z.  One barrier per
-// iteration (the filtered rows are double buffered); the global loads of the NEXT iteration's row are issued before
-// the barrier, so they are in flight while the V phase runs.
+// iteration (the filtered rows are double buffered).  The bytes of the NEXT iteration's row travel global -> shared
+// with cp.async (LDGSTS: no register staging) into a lane-private 80-byte slot, issued right after the H phase has
+// consumed the current ones: they are in flight across the barrier and the whole V phase without holding 18
+// registers per thread, which the V phase's register window needs (R = 3: 56 of the 128 a thread may have).
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src, bool valid) {  // zero fill when !valid
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+constexpr int kRawSlotBytes = 80;  // 3 own chunks + the 16 bytes before + the 16 bytes after; 5 x 16 B at a lane
+                                   // stride of 5 chunks: conflict free
+constexpr int kRawMaskBytes = 8;   // + the two mask words around the unit, in an array of their own
 template <int R, bool RAIN>
-__global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
+__global__ void __launch_bounds__(strip::Geo<R>::kThreads, strip::Geo<R>::kCtasPerSm)
     blur_strip_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, const AwxCorruptParams* __restrict__ params,
                       const unsigned* __restrict__ mask, int H, int W, int WW, int seg, float negzero) {
   using G = strip::Geo<R>;
@@ -535,7 +548,11 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
   if (prm.kind != (RAIN ? AWX_RAIN : AWX_SNOW) || prm.blur_k != 2 * R + 1) return;
 
   extern __shared__ __align__(16) unsigned char smem[];
-  float4* s_h = reinterpret_cast<float4*>(smem);  // [2][NR][G::kRowFloat4]
+  float4* s_h = reinterpret_cast<float4*>(smem);  // [G::kBuffers][NR][G::kRowFloat4]
+  uint4* s_raw = reinterpret_cast<uint4*>(smem + G::kSmemBytes) + threadIdx.x * (kRawSlotBytes / 16);  // this lane's slot
+  const uint32_t raw_addr = (uint32_t)__cvta_generic_to_shared(s_raw);
+  uint2* s_mask = reinterpret_cast<uint2*>(smem + G::kSmemBytes + G::kThreads * kRawSlotBytes) + threadIdx.x;
+  const uint32_t mask_addr = (uint32_t)__cvta_generic_to_shared(s_mask);
 
   const int NU = W / strip::kUnitPx;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -557,20 +574,34 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
   pp.t[3] = prm.taps[3];
   pp.negzero = negzero;
 
-  auto load_raw = [&](int hr, strip::Raw& r) {
+  // issue the copies of filtered row `hr` (nothing here waits on memory)
+  auto prefetch = [&](int hr) {
     const int sy = strip::reflect101(ys - R + hr, H);
     const uint8_t* g = src + (size_t)sy * row_bytes + (size_t)unit * strip::kUnitE;
-    const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(g)), c1 = __ldg(reinterpret_cast<const uint4*>(g + 16)),
-                c2 = __ldg(reinterpret_cast<const uint4*>(g + 32));
-    uint4 l = make_uint4(0, 0, 0, 0), rr = make_uint4(0, 0, 0, 0);
-    if (unit > 0) l = __ldg(reinterpret_cast<const uint4*>(g - 16));
-    if (unit + 1 < NU) rr = __ldg(reinterpret_cast<const uint4*>(g + 48));
+    cp_async16(raw_addr, g);
+    cp_async16(raw_addr + 16, g + 16);
+    cp_async16(raw_addr + 32, g + 32);
+    if (unit > 0) cp_async16(raw_addr + 48, g - 16);        // else: reflect_left fills the halo
+    if (unit + 1 < NU) cp_async16(raw_addr + 64, g + 48);   // else: reflect_right does
+    // the two mask words around the unit (see strip::mask_words), zero filled outside the row
+    const unsigned* mrow = m + (size_t)sy * WW;
+    const int wi = unit >> 1, w0 = (unit & 1) ? wi : wi - 1;
+    cp_async4(mask_addr, mrow + (w0 >= 0 ? w0 : 0), w0 >= 0);
+    cp_async4(mask_addr + 4, mrow + (w0 + 1 < WW ? w0 + 1 : 0), w0 + 1 < WW);
+    cp_async_commit();
+  };
+  // ... and collect them at the start of the H phase
+  auto collect = [&](strip::Raw& r) {
+    cp_async_wait_all();
+    const uint4 c0 = s_raw[0], c1 = s_raw[1], c2 = s_raw[2], l = s_raw[3], rr = s_raw[4];
     r.own[0] = c0.x, r.own[1] = c0.y, r.own[2] = c0.z, r.own[3] = c0.w;
     r.own[4] = c1.x, r.own[5] = c1.y, r.own[6] = c1.z, r.own[7] = c1.w;
     r.own[8] = c2.x, r.own[9] = c2.y, r.own[10] = c2.z, r.own[11] = c2.w;
     r.hl[0] = l.y, r.hl[1] = l.z, r.hl[2] = l.w;
     r.hr[0] = rr.x, r.hr[1] = rr.y, r.hr[2] = rr.z;
-    strip::mask_words(m + (size_t)sy * WW, unit, WW, r.m0, r.m1);
+    const uint2 mw = *s_mask;
+    r.m0 = mw.x, r.m1 = mw.y;
+    strip::finish_raw(r, unit, NU);
   };
 
   // V-phase ownership
@@ -583,7 +614,7 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
   uint8_t* vdst = dst + (size_t)vunit * strip::kUnitE + vkg * 4 + ((ptrdiff_t)ys - 2 * R) * (ptrdiff_t)row_bytes;
 
   strip::Raw raw;
-  if (hact && warp < nH) load_raw(warp, raw);
+  if (hact && warp < nH) prefetch(warp);
   strip::Window<R> win;
   constexpr unsigned kOvBits = ((1u << (strip::kUnitPx + 2 * R)) - 1u) << (8 - R);  // the pixels the filter can reach
 
@@ -597,7 +628,7 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
       rowbuf[strip::quad_slot(lane, q)] = make_float4(a.x, a.y, c.x, c.y);
     };
     // overlays are rare per pixel but not per warp: one vote picks the instruction stream with or without selects
-    if (hrow) strip::finish_raw(raw, unit, NU);
+    if (hrow) collect(raw);
     const bool any_ov = __any_sync(0xffffffffu, hrow && (raw.mb & kOvBits) != 0u);
     if (hrow) {
       if (any_ov)
@@ -605,7 +636,7 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
       else
         strip::h_row<R, RAIN, false>(raw, pp, store);
     }
-    if (hact && hr + NR < nH) load_raw(hr + NR, raw);
+    if (hact && hr + NR < nH) prefetch(hr + NR);
     __syncthreads();
     if (vact) {
       const float4* vb = s_h + (size_t)(buf * NR) * G::kRowFloat4;
@@ -627,7 +658,10 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, 2)
       AWX_VROW(0) AWX_VROW(1) AWX_VROW(2) AWX_VROW(3) AWX_VROW(4) AWX_VROW(5) AWX_VROW(6)
 #undef AWX_VROW
     }
-    buf ^= 1;
+    if (G::kBuffers == 2)
+      buf ^= 1;
+    else
+      __syncthreads();  // single buffer: the next H phase overwrites the rows this V phase read
   }
 }
 
@@ -636,12 +670,13 @@ int launch_blur_strip(const uint8_t* img, uint8_t* out, const AwxCorruptParams* 
                       int64_t n_match, int H, int W, int WW, cudaStream_t s) {
   using G = strip::Geo<R>;
   auto kern = blur_strip_kernel<R, RAIN>;
-  AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+  constexpr int kSmem = G::kSmemBytes + G::kThreads * (kRawSlotBytes + kRawMaskBytes);
+  AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   const int strips = (W / strip::kUnitPx + strip::kStripUnits - 1) / strip::kStripUnits;
   // Row segments: a CTA filters seg + 2R rows to emit seg, and the launch runs in waves of 2 CTAs per SM; pick the
   // segment count that minimises waves x rows per CTA (long segments amortise the vertical halo, short ones fill the
   // last wave), between 32 and 128 rows per segment.
-  const long long slots = 2LL * sm_count();
+  const long long slots = (long long)G::kCtasPerSm * sm_count();
   const long long lo = (H + 127) / 128, hi = H / 32 > 0 ? H / 32 : 1;
   long long best = lo, best_cost = -1;
   for (long long n = lo; n <= hi; ++n) {
@@ -651,7 +686,7 @@ int launch_blur_strip(const uint8_t* img, uint8_t* out, const AwxCorruptParams* 
   }
   const int seg = (int)((H + best - 1) / best);
   dim3 grid((unsigned)strips, (unsigned)((H + seg - 1) / seg), (unsigned)B);
-  kern<<<grid, G::kThreads, G::kSmemBytes, s>>>(img, out, dparams, mask, H, W, WW, seg, -0.0f);
+  kern<<<grid, G::kThreads, kSmem, s>>>(img, out, dparams, mask, H, W, WW, seg, -0.0f);
   AWX_CUDA(cudaGetLastError());
   note_launch();
   return AWX_OK;
