@@ -75,6 +75,8 @@ def measured_peak():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """nvidia-smi polled every 50 ms from BEFORE the warm-up (its start-up takes longer than a short timed region);
+    every line is stamped on arrival and `stop` keeps the samples that fall inside the marked region."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -83,12 +85,13 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -96,26 +99,42 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def begin_region(self):
+        self.t_begin = time.monotonic()
+
+    def end_region(self):
+        self.t_end = time.monotonic()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        t1 = self.t_end if self.t_end is not None else float("inf")
+        # a sample reports the state at some point of the 50 ms before it arrives
+        inside = [ln for t, ln in self.lines if t0 <= t <= t1 + 0.06]
+        where = "timed region"
+        if not inside and self.lines:   # region shorter than one polling interval: the sample nearest to it
+            mid = 0.5 * (t0 + min(t1, self.lines[-1][0]))
+            inside = [min(self.lines, key=lambda tl: abs(tl[0] - mid))[1]]
+            where = "nearest sample (region shorter than the 50 ms polling interval)"
+        sm, mx, power, reasons = [], None, [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
             try:
                 sm.append(float(parts[0]))
                 mx = float(parts[1])
+                power.append(float(parts[2]))
             except ValueError:
                 continue
             for name, val in zip(names, parts[3:7]):
@@ -123,7 +142,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "sampled": where, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------- CPU arm (the reference itself)
@@ -365,13 +384,14 @@ def run_gpu_arm(args, rank, world, local_rank):
         return float(t.item())
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         wl.step()
     wl.ev.reset()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.begin_region()
     wl.record_score_events = True
     launches0 = lib.awx_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -380,6 +400,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         wl.step()
     e1.record()
     barrier()
+    sampler.end_region()
     launches = lib.awx_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     wl.record_score_events = False
@@ -525,7 +546,11 @@ def run_sweep(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    run_one_sweep(wl, sweep_blocks(min(args.sweep_frames, 4 * args.batch * world), args.batch, rank, world))   # warm-up
+    barrier()
+    sampler.begin_region()
     m = measure_sweep(wl, args, args.sweep_frames, rank, world, barrier, max_over_ranks)
+    sampler.end_region()
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         cfg = workload_config(args)
@@ -593,6 +618,19 @@ def configs_object(wl, args, rank, world, barrier, max_over_ranks):
     m = measure_sweep(wl, args, 10000, rank, world, barrier, max_over_ranks)
     m.pop("results")
     out["c4_sweep"] = m
+    # the corruption kernels on their own (awx_corrupt on the step's batch and parameter pool; rain / snow include the
+    # overlay rasterisation and the mask memset): algorithmic bytes per pixel as in SURVEY 8d
+    cor = {}
+    pxb = float(args.batch * h * w)
+    for kind in CONDITIONS[1:]:
+        ms = time_launches(lambda: wl.ops.corrupt(wl.images, wl.params[kind], wl.fields[kind], wl.items[kind], out=wl.out,
+                                                  workspace=wl.workspace))
+        gbps = CORRUPT_BYTES_PER_PX[kind] * pxb / (ms * 1e-3) / 1e9
+        cor[kind] = {"ms": ms, "bytes_per_px": CORRUPT_BYTES_PER_PX[kind], "GBps": gbps, "frac_of_measured_peak": gbps / peak}
+    cor["kernels"] = {"fog": "fog_kernel (fp32 screen + fp64 exact path)", "rain": "blur_strip_kernel<1, rain>",
+                      "snow": "blur_strip_kernel<1 | 3, snow> (the pool's 3- and 7-tap frames in two launches)",
+                      "night": "pointwise_kernel<double>"}
+    out["corruption_batch"] = cor
     return out
 
 
