@@ -104,11 +104,12 @@ __global__ void __launch_bounds__(kPointThreads, 5) pointwise_kernel(const uint8
                                                                    uint8_t* __restrict__ out,
                                                                    const AwxCorruptParams* __restrict__ params,
                                                                    const FT* __restrict__ field, long long HW,
-                                                                   const __grid_constant__ NormOut norm, int fog_elsewhere) {
+                                                                   const __grid_constant__ NormOut norm, int fog_elsewhere /* bit 0: fog_kernel, bit 1: night_kernel take their images */) {
   const int b = blockIdx.y;
   const AwxCorruptParams prm = params[b];
   if (prm.kind != AWX_CLEAN && prm.kind != AWX_FOG && prm.kind != AWX_NIGHT) return;
-  if (prm.kind == AWX_FOG && fog_elsewhere && prm.field_offset % 2 == 0 && fog::params_ok(prm.d0, prm.d1)) return;  // fog_kernel has this image
+  if (prm.kind == AWX_FOG && (fog_elsewhere & 1) && prm.field_offset % 2 == 0 && fog::params_ok(prm.d0, prm.d1)) return;  // fog_kernel has this image
+  if (prm.kind == AWX_NIGHT && (fog_elsewhere & 2) && prm.field_offset % 2 == 0) return;                                   // night_kernel has it
   __shared__ __align__(16) unsigned s_in[kChunkPx * 3 / 4];
   __shared__ __align__(16) unsigned s_out[kChunkPx * 3 / 4];
   const uint8_t* src = img + (size_t)b * HW * 3;
@@ -257,6 +258,69 @@ __global__ void __launch_bounds__(kFogThreads, 3) fog_kernel(const uint8_t* __re
 // the screened fog kernel takes whole 16-pixel units of 16-byte aligned tensors
 bool fog_kernel_ok(const uint8_t* img, const uint8_t* out, const void* field, long long HW) {
   return HW % 16 == 0 && (((uintptr_t)img | (uintptr_t)out | (uintptr_t)field) & 15) == 0;
+}
+
+// ------------------------------------------------------------------------------------------ night, flat
+// Night is a pure element-wise map over the 3 H W values of a frame with a period-3 constant (the colour shift):
+//   out[i] = trunc(clip((double)fl(fl(fl(u[i] / 255) * gain) * shift[i % 3]) + noise[i] * (I / 2), 0, 1) * 255)
+// so the kernel ignores pixels altogether.  A warp owns 512 consecutive values per iteration; in load j (of 8) lane
+// l takes the PAIR 64 j + 2 l: one 16-byte load of two fp64 noise values (a warp reads 512 contiguous bytes per
+// instruction -- the 30 bytes per pixel are all noise, and they stream fully coalesced with all eight loads in
+// flight before the first use), one 2-byte load of the two input bytes, one 2-byte store.  No shared memory, no
+// barrier (the staged generic kernel: three barriers per 1024 pixels).  Arithmetic as in pointwise_kernel: fp32 dim and
+// shift, separately rounded; fp64 noise add; exact.  Needs an even number of values per frame, a 16-byte aligned
+// field and an even field offset; anything else goes to the generic kernel.
+constexpr int kNightThreads = 256;
+constexpr int kNightPairs = 8;                                  // pairs per lane and iteration
+constexpr int kNightBlockValues = kNightThreads * 2 * kNightPairs;  // 4096
+__global__ void __launch_bounds__(kNightThreads, 4) night_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
+                                                                  const AwxCorruptParams* __restrict__ params,
+                                                                  const double* __restrict__ field, long long HW) {
+  const int b = blockIdx.y;
+  const AwxCorruptParams prm = params[b];
+  if (prm.kind != AWX_NIGHT || (prm.field_offset & 1) != 0) return;  // the generic kernel has it
+  const long long N = HW * 3;
+  const uint8_t* src = img + (size_t)b * N;
+  uint8_t* dst = out + (size_t)b * N;
+  const double* fld = field + prm.field_offset;
+  const float gain = prm.f0;
+  const double half_i = prm.d0 * 0.5;  // noise * I * 0.5: the halving is exact, one fp64 multiply
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long base = (long long)blockIdx.x * kNightBlockValues; base < N; base += (long long)gridDim.x * kNightBlockValues) {
+    const long long i0 = base + warp * (64 * kNightPairs) + 2 * lane;  // this lane's first pair
+    double2 nz[kNightPairs];
+    unsigned short by[kNightPairs];
+#pragma unroll
+    for (int j = 0; j < kNightPairs; ++j) {
+      const long long i = i0 + 64 * j;
+      if (i < N) {
+        nz[j] = __ldg(reinterpret_cast<const double2*>(fld + i));
+        by[j] = __ldg(reinterpret_cast<const unsigned short*>(src + i));
+      }
+    }
+    // colour shifts rotated to this lane's phase: value i has channel i % 3, pair j starts at channel (c0 + j) % 3
+    const int c0 = (int)(i0 % 3);
+    const float sh0 = c0 == 0 ? 0.8f : (c0 == 1 ? 0.85f : 1.2f);
+    const float sh1 = c0 == 0 ? 0.85f : (c0 == 1 ? 1.2f : 0.8f);
+    const float sh2 = c0 == 0 ? 1.2f : (c0 == 1 ? 0.8f : 0.85f);
+    const float sh[3] = {sh0, sh1, sh2};
+#pragma unroll
+    for (int j = 0; j < kNightPairs; ++j) {
+      const long long i = i0 + 64 * j;
+      if (i < N) {
+        const float va = __fmul_rn(__fmul_rn(unit_of_u8(by[j] & 0xffu), gain), sh[j % 3]);
+        const float vb = __fmul_rn(__fmul_rn(unit_of_u8(by[j] >> 8), gain), sh[(j + 1) % 3]);
+        const unsigned ra = to_u8_f64(__dadd_rn((double)va, __dmul_rn(nz[j].x, half_i)));
+        const unsigned rb = to_u8_f64(__dadd_rn((double)vb, __dmul_rn(nz[j].y, half_i)));
+        *reinterpret_cast<unsigned short*>(dst + i) = (unsigned short)(ra | (rb << 8));
+      }
+    }
+  }
+}
+
+bool night_kernel_ok(const uint8_t* img, const uint8_t* out, const void* field, long long HW) {
+  const char* e = getenv("AWX_NIGHT_KERNEL");  // =staged: the generic kernel (A/B measurements, parity tests of both)
+  return !(e && e[0] == 's') && (HW * 3) % 2 == 0 && (((uintptr_t)img | (uintptr_t)out) & 1) == 0 && (((uintptr_t)field) & 15) == 0;
 }
 
 // --------------------------------------------------------------------------- rain / snow
@@ -771,7 +835,9 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
   const char* fog_env = getenv("AWX_FOG_KERNEL");
   const bool fog_fast = !(fog_env && fog_env[0] == 'e') && field_dtype == AWX_F64 && out != nullptr && norm.ptr == nullptr &&
                         fog_kernel_ok(img, out, field, (long long)H * W);
-  bool any_fog_fast = false;
+  const bool night_fast = field_dtype == AWX_F64 && out != nullptr && norm.ptr == nullptr &&
+                          night_kernel_ok(img, out, field, (long long)H * W);
+  bool any_fog_fast = false, any_night_fast = false;
   bool any_point = false, any_overlay = false;
   int64_t blur[4] = {0, 0, 0, 0};  // images per (kind, blur size): rain 3 / 7, snow 3 / 7
   for (int64_t b = 0; b < batch; ++b) {
@@ -782,6 +848,8 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
       case AWX_NIGHT:
         if (q.kind == AWX_FOG && fog_fast && q.field_offset % 2 == 0 && fog::params_ok(q.d0, q.d1))
           any_fog_fast = true;
+        else if (q.kind == AWX_NIGHT && night_fast && q.field_offset % 2 == 0)
+          any_night_fast = true;
         else
           any_point = true;
         AWX_REQUIRE(field != nullptr, AWX_E_ARG, "awx_corrupt: image %lld (fog/night) needs a depth/noise field", (long long)b);
@@ -810,7 +878,8 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
     const long long cap = (long long)sm_count() * 16;
     dim3 grid((unsigned)(chunks < cap ? chunks : cap), (unsigned)batch);
     if (field_dtype == AWX_F64)
-      pointwise_kernel<double><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW, norm, fog_fast ? 1 : 0);
+      pointwise_kernel<double><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW, norm,
+                                                              (fog_fast ? 1 : 0) | (night_fast ? 2 : 0));
     else
       pointwise_kernel<float><<<grid, kPointThreads, 0, s>>>(img, out, dparams, static_cast<const float*>(field), HW, norm, 0);
     AWX_CUDA(cudaGetLastError());
@@ -821,6 +890,14 @@ int corrupt_impl(const uint8_t* img, uint8_t* out, const NormOut& norm, int64_t 
     const long long cap = (long long)sm_count() * 12;
     dim3 grid((unsigned)(blocks < cap ? blocks : cap), (unsigned)batch);
     fog_kernel<<<grid, kFogThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW);
+    AWX_CUDA(cudaGetLastError());
+    note_launch();
+  }
+  if (any_night_fast) {
+    long long blocks = (HW * 3 + kNightBlockValues - 1) / kNightBlockValues;
+    const long long cap = (long long)sm_count() * 16;
+    dim3 grid((unsigned)(blocks < cap ? blocks : cap), (unsigned)batch);
+    night_kernel<<<grid, kNightThreads, 0, s>>>(img, out, dparams, static_cast<const double*>(field), HW);
     AWX_CUDA(cudaGetLastError());
     note_launch();
   }

@@ -53,3 +53,27 @@ def test_out_of_range_coefficients_fall_back_to_the_exact_kernel(wdt):
     d.depth = ow.depth_from_noise(d.depth_noise)
     got = t.corrupt_batch(imgs, [d]).cpu().numpy()[0]
     assert np.array_equal(got, ow.fog_apply(imgs[0], d.depth, d.intensity))
+
+
+@pytest.mark.parametrize("h,w,b", [(1024, 2048, 2), (96, 160, 3), (37, 54, 4), (5, 6, 2)])
+def test_flat_and_staged_night_kernels_agree_and_match_the_oracle(wdt, monkeypatch, h, w, b):
+    """night_kernel (flat element-wise, no shared memory) against the staged generic kernel (AWX_NIGHT_KERNEL=staged)
+    and the oracle: 0 LSB.  Batches mix kinds, so both point kernels and the fog kernel run side by side."""
+    t = wdt(seed=w + b)
+    rng = np.random.RandomState(h)
+    imgs = rng.randint(0, 256, (b, h, w, 3)).astype(np.uint8)
+    kinds = ["night", "fog", "night", "clean"][:b]
+    draws = [t.draw(k, h, w) for k in kinds]
+    for d in draws:
+        if d.kind == "fog":
+            d.depth = ow.depth_from_noise(d.depth_noise)
+    monkeypatch.delenv("AWX_NIGHT_KERNEL", raising=False)
+    a = t.corrupt_batch(imgs, draws)
+    monkeypatch.setenv("AWX_NIGHT_KERNEL", "staged")
+    c = t.corrupt_batch(imgs, draws)
+    assert torch.equal(a, c), f"{int((a != c).sum())} values differ between the flat and the staged night kernel"
+    a = a.cpu().numpy()
+    for i, d in enumerate(draws):
+        if d.kind == "night":
+            want = ow.night_apply(imgs[i], d.intensity, d.reduction, d.noise)
+            assert np.array_equal(a[i], want), f"image {i}: {int((a[i] != want).sum())} values differ from the oracle"
