@@ -27,6 +27,12 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Build knob AWX_WAIT_SLEEP_NS: back off that long after a failed attempt.  try_wait's suspend-time hint is only a hint
+// -- a consumer warp of the score kernel re-polls every ~40 cycles (93 SYNCS per pixel) -- so an explicit sleep trades
+// wake-up latency against ~150 issued instructions per pixel.  Measured: profiles/r2u_wait_backoff.md.
+#ifndef AWX_WAIT_SLEEP_NS
+#define AWX_WAIT_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, unsigned parity) {
   unsigned ok;
   do {
@@ -35,6 +41,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, unsigned parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
+    if (AWX_WAIT_SLEEP_NS > 0 && !ok) __nanosleep(AWX_WAIT_SLEEP_NS);
   } while (!ok);
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
