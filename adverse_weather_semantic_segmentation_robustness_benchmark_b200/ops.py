@@ -95,6 +95,12 @@ def normalise_labels(t: torch.Tensor) -> torch.Tensor:
     raise TypeError(f"labels must be an integer tensor, got {t.dtype}")
 
 
+@functools.lru_cache(maxsize=None)
+def _ece_edge_floats(num_bins: int) -> tuple:
+    """The edges as Python floats, once per bin count (score_config runs on every launch)."""
+    return tuple(float(e) for e in torch.linspace(0, 1, num_bins + 1).numpy())
+
+
 def ece_edges(num_bins: int) -> torch.Tensor:
     """Bin boundaries exactly as the reference builds them (evaluation/metrics.py:179)."""
     return torch.linspace(0, 1, num_bins + 1)
@@ -162,8 +168,7 @@ def score_config(num_classes: int, strategy: int, w0: float, w1: float, temperat
     cfg.label_dtype = label_dtype
     cfg.ignore_index = ignore_index
     cfg.ece_bins, cfg.auroc_bins, cfg.auroc_hi = ece_bins, auroc_bins, float(auroc_hi)
-    for i, e in enumerate(ece_edges(ece_bins).numpy()):
-        cfg.ece_edges[i] = float(e)
+    cfg.ece_edges[:ece_bins + 1] = _ece_edge_floats(ece_bins)
     return cfg
 
 

@@ -87,3 +87,47 @@ def assert_ens_wrong_parity(bins, wrong_ref: int, n_valid: int, _lib, per_pixel:
     diff = abs(bins.counter(_lib.CNT_ENS_WRONG) - int(wrong_ref))
     assert diff <= mamb, f"ensemble-wrong count differs by {diff}, only {mamb} pixels reported ambiguous"
     return {"ens_wrong_mismatch": diff, "marg_ambiguous": mamb}
+
+
+def cv2_blur_follows_the_restated_order() -> bool:
+    """Does THIS machine's cv2.GaussianBlur (CV_32FC3) follow the operation order csrc/blur_strip.cuh restates --
+    row filter fma(c, t0, fl((l + r) t1)) / left-to-right chain, column filter fl(c t0) then fma per tap pair?
+    OpenCV picks its filter kernels by CPU dispatch (and fuses multiply-adds only in FMA builds), so the 0-LSB bar of
+    the rain / snow images is asserted where a self-check on a random image says the order holds, the 1-LSB bar
+    elsewhere.  fma is emulated in fp64 (the product of two fp32 values is exact there)."""
+    import cv2
+    rng = np.random.RandomState(0)
+    h, w = 24, 48
+    img = rng.rand(h, w, 3).astype(np.float32)
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+    def mul(a, b):
+        return (a * np.float32(b)).astype(np.float32)
+
+    def pad(x, r, axis):
+        n = x.shape[axis]
+        lo = np.flip(np.take(x, range(1, r + 1), axis=axis), axis)
+        hi = np.flip(np.take(x, range(n - r - 1, n - 1), axis=axis), axis)
+        return np.concatenate([lo, x, hi], axis=axis)
+
+    for k, sigma in ((3, 0.5), (7, 1.0)):
+        r = k // 2
+        taps = cv2.getGaussianKernel(k, sigma, cv2.CV_32F).ravel()
+        t = [np.float32(taps[r + j]) for j in range(r + 1)]
+        p = pad(img, r, 1)
+        at = lambda q, off, axis, n: np.take(q, range(r + off, r + off + n), axis=axis)
+        if r == 1:
+            hres = fma(at(p, 0, 1, w), t[0], mul((at(p, -1, 1, w) + at(p, 1, 1, w)).astype(np.float32), t[1]))
+        else:
+            hres = mul(at(p, -r, 1, w), t[r])
+            for j in range(-r + 1, r + 1):
+                hres = fma(at(p, j, 1, w), t[abs(j)], hres)
+        q = pad(hres, r, 0)
+        v = mul(at(q, 0, 0, h), t[0])
+        for j in range(1, r + 1):
+            v = fma((at(q, -j, 0, h) + at(q, j, 0, h)).astype(np.float32), t[j], v)
+        if not np.array_equal(v, cv2.GaussianBlur(img, (k, k), sigma)):
+            return False
+    return True

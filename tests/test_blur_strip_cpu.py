@@ -17,6 +17,12 @@ import numpy as np
 import pytest
 
 from oracle import weather as ow
+from parity import cv2_blur_follows_the_restated_order
+
+# cv2 chooses its filter kernels by CPU dispatch; the emulation is compared bit for bit where this machine's cv2
+# follows the order the header restates (a self-check on a random image; true on every machine seen so far)
+pytestmark = pytest.mark.skipif(not cv2_blur_follows_the_restated_order(),
+                                reason="this machine's cv2.GaussianBlur uses another operation order")
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
