@@ -144,3 +144,39 @@ def test_full_size_properties(wdt):
     want = ow.rain_apply(imgs[2], draws[2].intensity, draws[2].items)
     mx, frac = _diff(a[2], want)
     assert mx <= 1 and frac < 1e-3
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (1, 2), (2, 1), (3, 3), (1, 16), (2, 16), (16, 1), (7, 17)])
+def test_tiny_frames_every_kind(wdt, h, w):
+    """Frames smaller than any filter support: BORDER_REFLECT_101 folds several times, a 1-pixel axis has no
+    neighbours at all.  Every kind against the oracle (the blur kernels switch between the strip and the tile form
+    with the width)."""
+    t = wdt(seed=h * 31 + w)
+    rng = np.random.RandomState(h + 7 * w)
+    kinds = ["fog", "rain", "snow", "snow", "night", "clean"]
+    imgs = rng.randint(0, 256, (len(kinds), h, w, 3)).astype(np.uint8)
+    draws = [t.draw(k, h, w) for k in kinds]
+    draws[2].blur_k, draws[3].blur_k = 3, 7
+    for d in draws:
+        if d.kind == "fog":
+            d.depth = ow.depth_from_noise(d.depth_noise)
+    out = t.corrupt_batch(imgs, draws).cpu().numpy()
+    for i, d in enumerate(draws):
+        if d.kind == "clean":
+            want = imgs[i]
+        elif d.kind == "fog":
+            want = ow.fog_apply(imgs[i], d.depth, d.intensity)
+        elif d.kind == "rain":
+            want = ow.rain_apply(imgs[i], d.intensity, d.items)
+        elif d.kind == "snow":
+            want = ow.snow_apply(imgs[i], d.intensity, d.items[:, :3], d.blur_k)
+        else:
+            want = ow.night_apply(imgs[i], d.intensity, d.reduction, d.noise)
+        mx, _ = _diff(out[i], want)
+        assert mx <= (0 if d.kind in ("clean", "fog", "night") else 1), (d.kind, h, w, mx)
+
+
+def test_empty_batch_is_a_no_op(wdt):
+    t = wdt(seed=0)
+    out = t.corrupt_batch(np.zeros((0, 8, 16, 3), np.uint8), [])
+    assert tuple(out.shape) == (0, 8, 16, 3) and out.dtype == torch.uint8
