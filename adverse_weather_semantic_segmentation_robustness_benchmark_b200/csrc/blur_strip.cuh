@@ -1,16 +1,17 @@
 // Row-walking separable Gaussian of the rain / snow corruptions (blur_strip_kernel in corrupt.cu).
 //
-// A CTA owns a STRIP of 32 units (a unit = 16 pixels = 48 bytes = 48 ELEMENTS of the HWC row) and walks down a
-// segment of rows, NR rows per iteration, every input row being read, point-op'ed and row-filtered exactly once:
+// A CTA owns a STRIP of 32 (3 taps) or 27 (7 taps) units -- a unit = 16 pixels = 48 bytes = 48 ELEMENTS of the HWC
+// row -- and walks down a segment of rows, NR rows per iteration, every input row being read, point-op'ed and
+// row-filtered exactly once:
 //
-//   H phase  warp w takes input row it*NR + w, lane = unit.  The lane loads its 48 bytes plus the 16 bytes before and
+//   H phase  thread tau takes (row it*NR + tau / units, unit tau % units): for 3 taps warp = row, lane = unit.  The lane loads its 48 bytes plus the 16 bytes before and
 //            after them (three pixels of halo each side; BORDER_REFLECT_101 at the image border is a byte shuffle of
 //            the lane's own unit), converts, applies the point operation and the overlay, and runs the horizontal
 //            filter ENTIRELY IN REGISTERS on 24 packed pairs {element k, element k + 24} -- both halves of a pair have
 //            the same channel and all tap offsets (multiples of 3 elements) shift k by whole pairs, so every operand
 //            is an aligned register pair: FMUL2 / FADD2 / FFMA2, two elements per issue slot.  The 24 filtered
 //            pairs go to shared memory as 12 conflict-free 16-byte stores.
-//   V phase  thread g (< 192) owns the 4 pairs {48u + 4kg + j, 48u + 24 + 4kg + j}, j < 4, of unit u = g / 6 for the
+//   V phase  thread g (< 6 x units) owns the 4 pairs {48u + 4kg + j, 48u + 24 + 4kg + j}, j < 4, of unit u = g / 6 for the
 //            whole walk: per row two 16-byte shared loads refill one slot of a (2R+1)-deep REGISTER window (the ring
 //            index is static: NR is a multiple of 2R+1), the vertical filter runs packed, and two 32-bit stores write
 //            the bytes (six lanes cover 24 contiguous bytes; the two stores of a warp interleave).
@@ -35,25 +36,45 @@ namespace strip {
 
 constexpr int kUnitPx = 16;
 constexpr int kUnitE = 48;
-constexpr int kStripUnits = 32;                       // units per strip: the lanes of an H-phase warp
-constexpr int kStripE = kStripUnits * kUnitE;         // 1536 elements
-constexpr int kGroups = kStripUnits * 6;              // V-phase threads (8 elements each)
-constexpr int kRowSlots = kGroups + kGroups / 24;     // float4 slots per half row: one pad slot per 4 units, so that the
-                                                      // H-phase stores (lane stride 6 slots) hit 8 distinct bank groups
+#ifndef AWX_STRIP_CTAS_R1
+#define AWX_STRIP_CTAS_R1 3   // build knob (CTAs per SM of the 3-tap kernels): 3 = 96 registers, no spills, 18 warps
+#endif
+#ifndef AWX_STRIP_CTAS_R3
+#define AWX_STRIP_CTAS_R3 2   // 7-tap kernels
+#endif
+#ifndef AWX_STRIP_UNITS_R3
+#define AWX_STRIP_UNITS_R3 27  // build knob (units per strip of the 7-tap kernels): 32 = 7 warps, 128 registers with
+                               // spills, 0.594 ms per 64 frames against 0.565
+#endif
 template <int R>
 struct Geo {
   static constexpr int kD = 2 * R + 1;                // window depth
-  static constexpr int kNR = R == 1 ? 6 : 7;          // rows per iteration = H-phase warps; a multiple of kD
-  static constexpr int kThreads = kNR * 32;
+  static constexpr int kNR = R == 1 ? 6 : 7;          // rows per iteration; a multiple of kD
+  // Units per strip.  H-phase task tau = threadIdx.x: row tau / kStripUnits of the iteration, unit tau % kStripUnits
+  // of the strip.  3 taps: 32 units, 6 x 32 = 192 tasks = 6 warps, warp = row.  7 taps: the register window alone is
+  // 56 registers, and a thread may only have 128 where a scheduler hosts 4 warps (2 CTAs of 7 warps: 14 warps on 4
+  // schedulers) -- which spilled ~40 words per thread and iteration.  27 units make 7 x 27 = 189 tasks fit 6 warps:
+  // 2 CTAs = 12 warps = 3 per scheduler = up to 168 registers, nothing spilled.
+  static constexpr int kStripUnits = R == 1 ? 32 : AWX_STRIP_UNITS_R3;
+  static constexpr int kGroups = kStripUnits * 6;     // V-phase threads (8 elements each)
+  static constexpr int kThreads = ((kNR * kStripUnits + 31) / 32) * 32;
+  // float4 slots per half row: one pad slot per 4 units, so that the H-phase stores (unit stride 6 slots) hit 8
+  // distinct bank groups; rounded up to a multiple of 8
+  static constexpr int kRowSlots = ((kGroups + (kStripUnits + 3) / 4 + 7) / 8) * 8;
   static constexpr int kRowFloat4 = 2 * kRowSlots;    // one filtered row in shared memory: [half][slot]
-  // R = 3: the filtered rows are double buffered, one barrier per iteration, 2 CTAs per SM (the register window needs
-  // 128 registers per thread anyway).  R = 1 gets by with 80 registers: a single buffer and a second barrier per
-  // iteration let 4 CTAs (24 warps) share an SM, which hides both barriers and the dependent-issue latencies.
+  // R = 3: the filtered rows are double buffered, one barrier per iteration, 2 CTAs per SM.  R = 1 gets by with far
+  // fewer registers: a single buffer and a second barrier per iteration let several CTAs share an SM, which hides both
+  // barriers and the dependent-issue latencies.  Measured per 64 frames, rain / snow-3: 2 CTAs 0.368 / 0.346 ms,
+  // 3 CTAs (96 registers, no spills) 0.322 / 0.299, 4 CTAs (80 registers, a few spilled loop scalars) 0.357 / 0.311.
   static constexpr int kBuffers = R == 1 ? 1 : 2;
-  static constexpr int kCtasPerSm = R == 1 ? 4 : 2;
+  static constexpr int kCtasPerSm = R == 1 ? AWX_STRIP_CTAS_R1 : AWX_STRIP_CTAS_R3;
   static constexpr int kSmemBytes = kBuffers * kNR * kRowFloat4 * 16;
   static_assert(kNR % kD == 0, "static ring index");
   static_assert(kThreads >= kGroups, "every V group has a thread");
+  // shared-memory slot (in float4 units, within one filtered row) of quad q = 2 * kg + h of unit u of the strip ...
+  AWX_HD static int quad_slot(int u, int q) { return (q & 1) * kRowSlots + 6 * u + (q >> 1) + (u >> 2); }
+  // ... and of V group g = 6 * u + kg, half h
+  AWX_HD static int group_slot(int g, int h) { return h * kRowSlots + g + g / 24; }
 };
 
 // ------------------------------------------------------------------------------------------------ packed pairs
@@ -262,11 +283,6 @@ AWX_HD void h_row(const Raw& raw, const PointParams& pp, Store&& store) {
     }
   }
 }
-
-// shared-memory slot (in float4 units, within one filtered row) of quad q = 2 * kg + h of unit u
-AWX_HD int quad_slot(int u, int q) { return (q & 1) * kRowSlots + 6 * u + (q >> 1) + (u >> 2); }
-// ... and of V group g = 6 * u + kg, half h
-AWX_HD int group_slot(int g, int h) { return h * kRowSlots + g + g / 24; }
 
 // ------------------------------------------------------------------------------------------------ V phase
 template <int R>

@@ -585,7 +585,7 @@ int launch_blur(const uint8_t* img, uint8_t* out, const AwxCorruptParams* dparam
 
 // ------------------------------------------------------------- rain / snow, row-walking strip kernel
 // blur_strip.cuh has the design and the per-thread code (shared with the host emulation of the tests).  This is the
-// CTA: strip = blockIdx.x (32 units = 512 pixels), row segment = blockIdx.y, image = blockIdx.z.  One barrier per
+// CTA: strip = blockIdx.x (32 or 27 units), row segment = blockIdx.y, image = blockIdx.z.  One barrier per
 // iteration (the filtered rows are double buffered).  The bytes of the NEXT iteration's row travel global -> shared
 // with cp.async (LDGSTS: no register staging) into a lane-private 80-byte slot, issued right after the H phase has
 // consumed the current ones: they are in flight across the barrier and the whole V phase without holding 18
@@ -619,9 +619,10 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, strip::Geo<R>::kCtasP
   const uint32_t mask_addr = (uint32_t)__cvta_generic_to_shared(s_mask);
 
   const int NU = W / strip::kUnitPx;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * strip::kStripUnits + lane;
-  const bool hact = unit < NU;
+  // H-phase task of this thread: row `hrl` of every iteration, unit `hul` of the strip
+  const int hrl = threadIdx.x / G::kStripUnits, hul = threadIdx.x - hrl * G::kStripUnits;
+  const int unit = blockIdx.x * G::kStripUnits + hul;
+  const bool hact = hrl < NR && unit < NU;
   const int ys = blockIdx.y * seg, ye = min(ys + seg, H);
   const int nH = ye - ys + 2 * R;  // filtered rows this CTA produces: ys - R .. ye + R - 1 (reflected)
   const size_t row_bytes = (size_t)W * 3;
@@ -671,25 +672,25 @@ __global__ void __launch_bounds__(strip::Geo<R>::kThreads, strip::Geo<R>::kCtasP
   // V-phase ownership
   const int g = threadIdx.x;
   const int vu = g / 6, vkg = g - vu * 6;
-  const int vunit = blockIdx.x * strip::kStripUnits + vu;
-  const bool vact = g < strip::kGroups && vunit < NU;
-  const int vslot0 = strip::group_slot(g < strip::kGroups ? g : 0, 0), vslot1 = strip::group_slot(g < strip::kGroups ? g : 0, 1);
+  const int vunit = blockIdx.x * G::kStripUnits + vu;
+  const bool vact = g < G::kGroups && vunit < NU;
+  const int vslot0 = G::group_slot(g < G::kGroups ? g : 0, 0), vslot1 = G::group_slot(g < G::kGroups ? g : 0, 1);
   // the thread's output pointer walks down the rows: row ys - 2R (virtual) at the first filtered row
   uint8_t* vdst = dst + (size_t)vunit * strip::kUnitE + vkg * 4 + ((ptrdiff_t)ys - 2 * R) * (ptrdiff_t)row_bytes;
 
   strip::Raw raw;
-  if (hact && warp < nH) prefetch(warp);
+  if (hact && hrl < nH) prefetch(hrl);
   strip::Window<R> win;
   constexpr unsigned kOvBits = ((1u << (strip::kUnitPx + 2 * R)) - 1u) << (8 - R);  // the pixels the filter can reach
 
   const int iters = (nH + NR - 1) / NR;
   int buf = 0;
   for (int it = 0; it < iters; ++it) {
-    const int hr = it * NR + warp;
+    const int hr = it * NR + hrl;
     const bool hrow = hact && hr < nH;
-    float4* rowbuf = s_h + (size_t)(buf * NR + warp) * G::kRowFloat4;
+    float4* rowbuf = s_h + (size_t)(buf * NR + (hrl < NR ? hrl : 0)) * G::kRowFloat4;
     auto store = [&](int q, const strip::F2& a, const strip::F2& c) {
-      rowbuf[strip::quad_slot(lane, q)] = make_float4(a.x, a.y, c.x, c.y);
+      rowbuf[G::quad_slot(hul, q)] = make_float4(a.x, a.y, c.x, c.y);
     };
     // overlays are rare per pixel but not per warp: one vote picks the instruction stream with or without selects
     if (hrow) collect(raw);
@@ -736,7 +737,7 @@ int launch_blur_strip(const uint8_t* img, uint8_t* out, const AwxCorruptParams* 
   auto kern = blur_strip_kernel<R, RAIN>;
   constexpr int kSmem = G::kSmemBytes + G::kThreads * (kRawSlotBytes + kRawMaskBytes);
   AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-  const int strips = (W / strip::kUnitPx + strip::kStripUnits - 1) / strip::kStripUnits;
+  const int strips = (W / strip::kUnitPx + G::kStripUnits - 1) / G::kStripUnits;
   // Row segments: a CTA filters seg + 2R rows to emit seg, and the launch runs in waves of 2 CTAs per SM; pick the
   // segment count that minimises waves x rows per CTA (long segments amortise the vertical halo, short ones fill the
   // last wave), between 32 and 128 rows per segment.

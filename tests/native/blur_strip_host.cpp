@@ -39,18 +39,19 @@ void run_cta(const uint8_t* src, uint8_t* dst, const unsigned* m, int H, int W, 
   };
 
   for (int t = 0; t < G::kThreads; ++t) {
-    const int warp = t >> 5, unit = strip * kStripUnits + (t & 31);
-    if (unit < NU && warp < nH) load_raw(warp, unit, raw[t]);
+    const int hrl = t / G::kStripUnits, unit = strip * G::kStripUnits + t % G::kStripUnits;
+    if (hrl < NR && unit < NU && hrl < nH) load_raw(hrl, unit, raw[t]);
   }
   const int iters = (nH + NR - 1) / NR;
   int buf = 0;
   for (int it = 0; it < iters; ++it) {
     for (int t = 0; t < G::kThreads; ++t) {  // H phase
-      const int warp = t >> 5, lane = t & 31, unit = strip * kStripUnits + lane;
-      const int hr = it * NR + warp;
+      const int hrl = t / G::kStripUnits, hul = t % G::kStripUnits, unit = strip * G::kStripUnits + hul;
+      if (hrl >= NR) continue;
+      const int hr = it * NR + hrl;
       const bool hrow = unit < NU && hr < nH;
-      Quad* rowbuf = s_h.data() + (size_t)(buf * NR + warp) * G::kRowFloat4;
-      auto store = [&](int q, const F2& a, const F2& c) { rowbuf[quad_slot(lane, q)] = Quad{a.x, a.y, c.x, c.y}; };
+      Quad* rowbuf = s_h.data() + (size_t)(buf * NR + hrl) * G::kRowFloat4;
+      auto store = [&](int q, const F2& a, const F2& c) { rowbuf[G::quad_slot(hul, q)] = Quad{a.x, a.y, c.x, c.y}; };
       if (hrow) {
         finish_raw(raw[t], unit, NU);
         // the device votes per warp; both instruction streams give the same values, so the emulation picks per lane
@@ -62,8 +63,8 @@ void run_cta(const uint8_t* src, uint8_t* dst, const unsigned* m, int H, int W, 
       }
       if (unit < NU && hr + NR < nH) load_raw(hr + NR, unit, raw[t]);
     }
-    for (int g = 0; g < kGroups; ++g) {  // V phase (after the barrier)
-      const int vu = g / 6, vkg = g - vu * 6, vunit = strip * kStripUnits + vu;
+    for (int g = 0; g < G::kGroups; ++g) {  // V phase (after the barrier)
+      const int vu = g / 6, vkg = g - vu * 6, vunit = strip * G::kStripUnits + vu;
       if (vunit >= NU) continue;
       const Quad* vb = s_h.data() + (size_t)(buf * NR) * G::kRowFloat4;
       uint8_t* vdst = dst + (size_t)vunit * kUnitE + vkg * 4;
@@ -74,7 +75,7 @@ void run_cta(const uint8_t* src, uint8_t* dst, const unsigned* m, int H, int W, 
           if (hj < nH) {
             unsigned wlo = 0, whi = 0;
             const bool emit = hj >= 2 * R;
-            v_row<R, J>(win[g], vb[J * G::kRowFloat4 + group_slot(g, 0)], vb[J * G::kRowFloat4 + group_slot(g, 1)], pp.t, emit,
+            v_row<R, J>(win[g], vb[J * G::kRowFloat4 + G::group_slot(g, 0)], vb[J * G::kRowFloat4 + G::group_slot(g, 1)], pp.t, emit,
                         wlo, whi);
             if (emit) {
               uint8_t* d = vdst + (size_t)(ys + hj - 2 * R) * row_bytes;
@@ -98,7 +99,7 @@ void run_cta(const uint8_t* src, uint8_t* dst, const unsigned* m, int H, int W, 
 
 template <int R, bool RAIN>
 void run_image(const uint8_t* src, uint8_t* dst, const unsigned* m, int H, int W, int WW, int seg, const PointParams& pp) {
-  const int strips = (W / kUnitPx + kStripUnits - 1) / kStripUnits;
+  const int strips = (W / kUnitPx + Geo<R>::kStripUnits - 1) / Geo<R>::kStripUnits;
   for (int s = 0; s < strips; ++s)
     for (int ys = 0; ys < H; ys += seg) run_cta<R, RAIN>(src, dst, m, H, W, WW, s, ys, seg, pp);
 }
