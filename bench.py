@@ -439,21 +439,25 @@ def run_gpu_arm(args, rank, world, local_rank):
         peak, peak_src = measured_peak()
         px_launch = float(args.batch * args.height * args.width)
         achieved = SCORE_BYTES_PER_PX * px_launch / (score_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "score_kernel_summary.json")) as fh:
-                summ = json.load(fh)
-            if summ.get("pixels_per_launch") == px_launch:
-                traffic = summ.get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        # dram__bytes_read + write of one launch of this kernel at this size, from the newest committed `ncu --set full`
+        # capture (round 2's kernel: profiles/r2d_score_g3_summary.json; ncu cannot run inside a timed benchmark)
+        traffic, traffic_src = None, None
+        for name in ("r2d_score_g3_summary.json", "score_kernel_summary.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", name)) as fh:
+                    summ = json.load(fh)
+                if summ.get("pixels_per_launch") == px_launch:
+                    traffic, traffic_src = summ.get("dram_bytes_per_launch"), "profiles/" + name
+                    break
+            except Exception:
+                pass
         step_bytes = sum((SCORE_BYTES_PER_PX + CORRUPT_BYTES_PER_PX[k]) for k in CONDITIONS) * px_launch
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(args),
             "roofline": {"bound": "hbm", "kernel": "score_v2_kernel<weighted,u8 labels,bins only> (awx_score)", "timed_launch": "the clean condition's launch of every timed step (the four others run the same kernel behind their corruption kernels inside awx_corrupt_score)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": SCORE_BYTES_PER_PX * px_launch,
                          "ms_per_launch": score_ms,
                          "whole_step_GBps": step_bytes / (ms_step * 1e-3) / 1e9},
