@@ -88,9 +88,10 @@ def test_screen_alone_is_right_where_it_does_not_flag(lib):
     assert wrong.sum() <= n, "the screen mis-decided a pixel it did not flag"
 
 
-@pytest.mark.parametrize("rel", [-4.8e-7, -2.4e-7, 2.4e-7, 4.8e-7])
+@pytest.mark.parametrize("rel", [-1e-6, -4.8e-7, -2.4e-7, 2.4e-7, 4.8e-7, 1e-6])
 def test_bytes_do_not_depend_on_the_transmission_approximation(lib, rel):
-    """ex2.approx is good to 2 ulp (2.4e-7); the band leaves room for twice that on top of the other terms."""
+    """ex2.approx is good to 2 ulp (2.4e-7); the band leaves room for several times that on top of the other terms
+    (a soak over 38 M values per level: no byte changes up to an injected 1.5e-6, the first ones at 2e-6)."""
     rng = np.random.RandomState(11)
     h, w = 256, 512
     img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
