@@ -738,7 +738,7 @@ int launch_blur_strip(const uint8_t* img, uint8_t* out, const AwxCorruptParams* 
   constexpr int kSmem = G::kSmemBytes + G::kThreads * (kRawSlotBytes + kRawMaskBytes);
   AWX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   const int strips = (W / strip::kUnitPx + G::kStripUnits - 1) / G::kStripUnits;
-  // Row segments: a CTA filters seg + 2R rows to emit seg, and the launch runs in waves of 2 CTAs per SM; pick the
+  // Row segments: a CTA filters seg + 2R rows to emit seg, and the launch runs in waves of kCtasPerSm CTAs per SM; pick the
   // segment count that minimises waves x rows per CTA (long segments amortise the vertical halo, short ones fill the
   // last wave), between 32 and 128 rows per segment.
   const long long slots = (long long)G::kCtasPerSm * sm_count();
