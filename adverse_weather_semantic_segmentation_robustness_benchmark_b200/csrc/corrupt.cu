@@ -219,8 +219,16 @@ __global__ void __launch_bounds__(kPointThreads, 5) pointwise_kernel(const uint8
 // 48 bytes out -- all eleven loads are issued before the first use, and consecutive lanes touch consecutive units, so
 // every warp-wide access is contiguous.  Needs H*W % 16 == 0 and 16-byte aligned tensors; anything else goes to the
 // generic kernel.
-constexpr int kFogThreads = 256;
-__global__ void __launch_bounds__(kFogThreads, 3) fog_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
+// build knobs; measured per 64 frames: 256 threads x 3 CTAs per SM 0.386 ms, x 4 (64 registers, spills) 0.410, x 5 0.447,
+// 128 threads x 6 (the same 24 warps in smaller CTAs: faster turnover, a thread handles one unit and exits) 0.352
+#ifndef AWX_FOG_THREADS
+#define AWX_FOG_THREADS 128
+#endif
+#ifndef AWX_FOG_CTAS
+#define AWX_FOG_CTAS 6
+#endif
+constexpr int kFogThreads = AWX_FOG_THREADS;
+__global__ void __launch_bounds__(kFogThreads, AWX_FOG_CTAS) fog_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
                                                               const AwxCorruptParams* __restrict__ params,
                                                               const double* __restrict__ field, long long HW) {
   const int b = blockIdx.y;
@@ -270,10 +278,13 @@ bool fog_kernel_ok(const uint8_t* img, const uint8_t* out, const void* field, lo
 // barrier (the staged generic kernel: three barriers per 1024 pixels).  Arithmetic as in pointwise_kernel: fp32 dim and
 // shift, separately rounded; fp64 noise add; exact.  Needs an even number of values per frame, a 16-byte aligned
 // field and an even field offset; anything else goes to the generic kernel.
-constexpr int kNightThreads = 256;
+#ifndef AWX_NIGHT_THREADS
+#define AWX_NIGHT_THREADS 256
+#endif
+constexpr int kNightThreads = AWX_NIGHT_THREADS;
 constexpr int kNightPairs = 8;                                  // pairs per lane and iteration
 constexpr int kNightBlockValues = kNightThreads * 2 * kNightPairs;  // 4096
-__global__ void __launch_bounds__(kNightThreads, 4) night_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
+__global__ void __launch_bounds__(kNightThreads, 1024 / kNightThreads) night_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
                                                                   const AwxCorruptParams* __restrict__ params,
                                                                   const double* __restrict__ field, long long HW) {
   const int b = blockIdx.y;
